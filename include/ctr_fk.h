@@ -1,0 +1,201 @@
+/* ctr_fk.h — C ABI of the B200 batched forward-kinematics engine for concentric
+ * tube robots (CTR).
+ *
+ * This is the drop-in boundary.  Everything above it (the C++14 `ctrb200::Robot`
+ * host object, Python ctypes bindings, a maintainer's patch to the reference's
+ * `CTR::Robot<Real>`) talks to the CUDA kernels only through these entry points:
+ * plain pointers and sizes, no C++ or torch types.
+ *
+ * Reference interfaces replaced (all paths relative to /root/reference/ctr_source):
+ *   - RobotBase::calcKinematic(VectorJ, Real step, Real& stepRet)      robot_i.h:223, :690-721
+ *   - RobotBase::calcKinematic(VectorJ, size_t NSamples, Real& stepRet) robot_i.h:226, :722-755
+ *   - Robot::calcKinematic(Real* JV, const Real& step, Real* Tr)        ctr_robot.cpp:166-186
+ *     (the raw-pointer form: JV array in, 3x4 column-major transform out) — ctr_fk_batch is
+ *     this call over B joint vectors at once.
+ *   - getNSamples/getTransformSample/getRadiusSample/getTip*            robot_i.h:520-533
+ *     -> the optional backbone / radius / n_out outputs.
+ *   - copy2opencl(local_constant_mem) robot descriptor                  robot_i.h:658-686
+ *     -> ctr_robot_desc (same fields, InitTrafo column-major).
+ *   - calcJacobian (finite differences, NSamples form)                  robot_i.h:917-960
+ *     -> ctr_fk_jacobian_batch.
+ *   - getRandomJointValues                                              robot_i.h:1308-1317,
+ *                                                                       section_i.h:328-337
+ *     -> ctr_fk_sample_joints (counter-based instead of mt19937; same distribution).
+ *
+ * Conventions
+ *   - Joint vector layout (robot_i.h:1126, section_i.h:204-209):
+ *       jv[0] = RigidTheta; per section s: jv[1+s+t0] = Phi_s, jv[2+s+t0+k] = AlphaTip of
+ *       tube k of the section (t0 = number of tubes in earlier sections).
+ *       n_jv = 1 + nsections + ntubes.
+ *   - Transforms are 12 doubles, column-major 3x4: r00 r10 r20 r01 r11 r21 r02 r12 r22 tx ty tz
+ *     (Erl::Transform::getData(.., ColMajor), ctr_robot.cpp:171).
+ *   - mode CTR_FK_MODE_STEP   : calcKinematic(JV, ArcLengthStep)  — N = floor(sum(Phi)/step)
+ *     mode CTR_FK_MODE_NSAMPLE: calcKinematic(JV, NSamples)       — N = min(NSamples, MaxSamples)
+ *   - Return value: 0 = OK, <0 = CTR_FK_E_* (bad argument / descriptor), >0 = cudaError_t.
+ *     No exceptions cross this boundary.  ctr_fk_last_error() gives a thread-local message.
+ *   - There is NO CPU fallback: every compute entry point fails with a CUDA error code when
+ *     no device is usable.
+ */
+#ifndef CTR_FK_H
+#define CTR_FK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_FK_MAX_SECTIONS 3   /* CTR_MAXSECTION, CMakeLists.txt:26-27 */
+#define CTR_FK_MAX_TUBES    6   /* 2 tubes per section at most, ctr_static.h:162 */
+#define CTR_FK_MAX_JV      (1 + CTR_FK_MAX_SECTIONS + CTR_FK_MAX_TUBES)
+
+#define CTR_FK_MODE_STEP    0
+#define CTR_FK_MODE_NSAMPLE 1
+
+/* flags for ctr_fk_batch* */
+#define CTR_FK_FLAG_STRICT     1u  /* reference operation order, libm-grade sin/cos/div/sqrt   */
+#define CTR_FK_FLAG_NO_BINNING 2u  /* step mode: do not sort configurations by sample count    */
+#define CTR_FK_FLAG_SOA        4u  /* backbone laid out [k][12][B] instead of [B][MaxS][12]     */
+
+/* error codes (<0) */
+#define CTR_FK_E_NULL      -1   /* null handle / required pointer                               */
+#define CTR_FK_E_DESC      -2   /* invalid robot descriptor                                     */
+#define CTR_FK_E_ARG       -3   /* invalid argument (mode, step<=0, nsamples<1, B<0 ...)         */
+#define CTR_FK_E_XML       -4   /* XML file unreadable or malformed                             */
+#define CTR_FK_E_NOMEM     -5   /* host allocation failed                                       */
+
+/* per-configuration status bits written to the optional `status` output */
+#define CTR_FK_STATUS_OK        0
+#define CTR_FK_STATUS_PHI_RANGE 1   /* some Phi outside [0, Length] (reference: assert, section_i.h:205);
+                                       outputs for that configuration are NaN                 */
+
+/* One section = 1 tube (CC) or 2 tubes (VC), section_i.h:365-369. */
+typedef struct ctr_section_desc {
+    int32_t ntube;          /* 1 or 2 */
+    int32_t reserved;
+    double  length;         /* m_Length                                     */
+    double  stiffness[2];   /* m_Stiffness      (entry [1] unused for CC)   */
+    double  curvature[2];   /* m_Curvature      (only [0] enters the FK, section_i.h:320-325) */
+    double  radius[2];      /* m_Radius         ([0] is the outer radius, section_i.h:151)    */
+    double  poisson[2];     /* m_PoissonRatio                               */
+} ctr_section_desc;
+
+/* Robot descriptor; mirrors RobotCCPP of copy2opencl(local_constant_mem), robot_i.h:658-686. */
+typedef struct ctr_robot_desc {
+    int32_t nsections;      /* 1..3 */
+    int32_t max_samples;    /* m_MaxSamples (>=1) */
+    double  init_trafo[12]; /* m_InitTrafo, column-major 3x4, already orthogonalised            */
+    double  zero_tol;       /* tolerance of Erl::equal(norm,0) in curvature2Transform
+                               (robot_i.h:1245); 0 selects the default 1e-12                    */
+    ctr_section_desc sec[CTR_FK_MAX_SECTIONS];
+} ctr_robot_desc;
+
+typedef struct ctr_fk_engine* ctr_fk_handle;
+
+/* ---- descriptor helpers (host only, no CUDA) --------------------------------------------- */
+
+/* Parse a ctr_resources XML file (V1 schema ctr_static.h:132-208, V2 schema :461-532, version
+ * sniff :594-601).  phi_xml (nullable, CTR_FK_MAX_SECTIONS doubles) receives the per-section
+ * <phi> values used for the construction-time FK (ctr_static.h:179,188,248-252). */
+int ctr_fk_desc_from_xml(const char* path, int32_t max_samples, ctr_robot_desc* out, double* phi_xml);
+/* Validate a descriptor (section count, tube counts, positive stiffness sums ...). */
+int ctr_fk_desc_validate(const ctr_robot_desc* desc);
+int ctr_fk_desc_ntubes(const ctr_robot_desc* desc);
+int ctr_fk_desc_njoints(const ctr_robot_desc* desc);          /* getNJoints, robot_i.h:522 */
+double ctr_fk_desc_max_length(const ctr_robot_desc* desc);    /* getMaxLength, robot_i.h:537-543 */
+/* Nearest rotation (polar factor) of the 3x3 part of a column-major 3x4 transform, in place;
+ * stands in for Erl::Transform::nearestOrthogonal (ctr_static.h:206).  Returns CTR_FK_E_ARG if
+ * max|R^T R - I| exceeds `verify_tol` before projection (verifyOrthogonal, ctr_static.h:202). */
+int ctr_fk_orthogonalize(double* trafo12, double verify_tol);
+
+/* ---- engine lifetime ------------------------------------------------------------------- */
+
+int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out);
+int ctr_fk_destroy(ctr_fk_handle h);
+int ctr_fk_get_desc(ctr_fk_handle h, ctr_robot_desc* out);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+
+/* Batched FK, DEVICE pointers (all on the handle's device), asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   jv        [B][n_jv]               in
+ *   tip       [B][12]                 out, nullable: m_CentreLineTransform[m_Samples-1]
+ *   backbone  [B][max_samples][12]    out, nullable: m_CentreLineTransform[0..n_out)
+ *                                     (or [max_samples][12][B] with CTR_FK_FLAG_SOA);
+ *                                     entries k >= n_out are unspecified (used as scratch)
+ *   radius    [B][max_samples]        out, nullable: m_CentreLineRadius (needs backbone != NULL
+ *                                     or may be requested alone)
+ *   n_out     [B]                     out, nullable: m_Samples
+ *   step_out  [B]                     out, nullable: _ArcLengthStepReturn
+ *   alpha_base[B][ntubes]             out, nullable: m_SampleTubeAlpha after the sweep (the tube
+ *                                     angles at the base; what calcStability reads, robot_i.h:810)
+ *   status    [B]                     out, nullable: CTR_FK_STATUS_* bits
+ */
+int ctr_fk_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                 int32_t nsamples, uint32_t flags,
+                 double* tip, double* backbone, double* radius, int32_t* n_out,
+                 double* step_out, double* alpha_base, int32_t* status, void* stream);
+
+/* Same computation with state arithmetic in FP32 (sample count, arc positions and the section
+ * masks stay FP64 so that n_out matches the FP64 path exactly).  Inputs/outputs stay double. */
+int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                     int32_t nsamples, uint32_t flags,
+                     double* tip, int32_t* n_out, double* step_out, int32_t* status, void* stream);
+
+/* Batched FK with HOST pointers (pageable or pinned).  The batch is cut into chunks that are
+ * copied in, solved and copied out on rotating streams so that PCIe transfers overlap the
+ * kernels.  Synchronous: returns when all outputs are in host memory.  Only tip / n_out /
+ * step_out / status are offered here (backbone output is 26 KB per configuration and is meant to
+ * stay on the device). */
+int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                      int32_t nsamples, uint32_t flags,
+                      double* tip, int32_t* n_out, double* step_out, int32_t* status);
+
+/* One configuration, HOST pointers, synchronous: the reference's single-shot call
+ * (robot_i.h:690-755) served by the same kernels with B = 1.  The handle keeps a small device
+ * scratch for it; calls on one handle are serialised.  backbone [max_samples][12], radius
+ * [max_samples]; every output nullable. */
+int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int32_t nsamples,
+                  uint32_t flags, double* tip, double* backbone, double* radius, int32_t* n_out,
+                  double* step_out, double* alpha_base);
+
+/* Batched finite-difference tip Jacobian, NSamples form (robot_i.h:917-960): 6 x n_jv,
+ * column-major per configuration: jac[B][n_jv][6].  DEVICE pointers.  tip nullable. */
+int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples,
+                          double fd_trans, double fd_rot, double* jac, double* tip, void* stream);
+
+/* The same with HOST pointers (synchronous; staged through the device). */
+int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples,
+                         double fd_trans, double fd_rot, double* jac, double* tip);
+
+/* ---- inputs ---------------------------------------------------------------------------- */
+
+/* Fill jv[B][n_jv] (DEVICE pointer) with the distribution of getRandomJointValues
+ * (robot_i.h:1308-1317): theta, alpha = nextafter(2*pi,0)*u, phi_s = Length_s*u, u~U[0,1).
+ * u for (config i, slot j) is splitmix64-derived from (seed, first_config + i, j) so any shard
+ * of a batch can be generated independently and reproducibly. */
+int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B,
+                         double* jv, void* stream);
+/* The same generator on the host (no CUDA). */
+int ctr_fk_sample_joints_host(const ctr_robot_desc* desc, uint64_t seed, int64_t first_config,
+                              int64_t B, double* jv);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+
+/* Sample count (m_Samples before the position-driven forward loop), host side, bit-identical to
+ * the kernel: used by bench.py to compute the algorithmic flop count of a step-mode batch. */
+int ctr_fk_count_samples_host(const ctr_robot_desc* desc, const double* jv, int64_t B, int mode,
+                              double step, int32_t nsamples, int32_t* n);
+/* FP64 FMA-pipe peak probe: runs independent DFMA chains on every SM for `iters` iterations on
+ * `stream` and returns the number of flops issued (2 per DFMA per lane).  Time it with events. */
+int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* stream);
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t ctr_fk_launch_count(void);
+
+const char* ctr_fk_last_error(void);
+const char* ctr_fk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTR_FK_H */

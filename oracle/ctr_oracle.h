@@ -1,0 +1,56 @@
+/* ctr_oracle.h — CPU oracle of the reference forward kinematics.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (libctrfk.so) never links, loads or calls it.
+ *
+ * PARITY UNPINNED: the reference (RViMLab/RAM2017-CTR-kinematics) ships no tests, golden vectors
+ * or fixtures for this path, and it cannot be compiled here (Eigen 3.3.3, Erl and Boost
+ * property_tree are fetched from the network by install.sh:41,49,59 and are absent).  This file
+ * is a step-for-step restatement of robot_i.h / section_i.h; it is pinned only against (a) an
+ * independent pure-Python restatement (oracle/ctr_oracle_py.py), (b) the sanity vectors of
+ * SURVEY.md §9.2 and (c) closed-form known-answer tests (tests/test_oracle.py).
+ */
+#ifndef CTR_ORACLE_H
+#define CTR_ORACLE_H
+
+#include <stdint.h>
+#include "../include/ctr_fk.h"   /* ctr_robot_desc (POD only) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One configuration.  All outputs nullable.
+ *   tip12      : m_CentreLineTransform[m_Samples-1], column-major 3x4
+ *   backbone   : [max_samples][12], entries [0, n_out) written
+ *   radius     : [max_samples]
+ *   curv       : [max_samples][3]  m_CurvatureInnermostTube (u_x,u_y,u_z per sample)
+ *   alpha_samp : [max_samples]     m_AlphaInnermostTube(:,0)
+ *   alpha_base : [ntubes]          m_SampleTubeAlpha after the sweep
+ * Returns CTR_FK_STATUS_* (0 = OK) or a negative CTR_FK_E_* code. */
+int ctr_oracle_fk(const ctr_robot_desc* desc, const double* jv, int mode, double step,
+                  int32_t nsamples, double* tip12, double* backbone, double* radius,
+                  int32_t* n_out, double* step_out, double* curv, double* alpha_samp,
+                  double* alpha_base);
+
+/* B configurations with `nthreads` OpenMP threads (one scratch per thread, mirroring the
+ * one-Robot-per-thread usage of the reference).  backbone [B][max_samples][12] etc. */
+int ctr_oracle_fk_batch(const ctr_robot_desc* desc, const double* jv, int64_t B, int mode,
+                        double step, int32_t nsamples, int nthreads, double* tip,
+                        double* backbone, double* radius, int32_t* n_out, double* step_out,
+                        double* alpha_base, int32_t* status);
+
+/* Finite-difference tip Jacobian, robot_i.h:917-960 + :41-56.  jac[n_jv][6] column-major 6 x n_jv. */
+int ctr_oracle_jacobian(const ctr_robot_desc* desc, const double* jv, int32_t nsamples,
+                        double fd_trans, double fd_rot, double* jac, double* tip12);
+
+/* calcStability, robot_i.h:756-818.  Returns 1 stable, 0 unstable, <0 error. */
+int ctr_oracle_stability(const ctr_robot_desc* desc, const double* jv, double angle_step,
+                         double arc_step);
+
+int ctr_oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,413 @@
+// ctr_fk_api.cu — the extern "C" boundary (include/ctr_fk.h) over the CUDA kernels.
+// No CPU fallback anywhere in this file: if a device call fails the CUDA error code is returned.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/ctr_fk.h"
+#include "../host/ctr_sampler.h"
+#include "ctr_fk_internal.h"
+#include "ctr_fk_krobot.h"
+#include "ctr_fk_launch.h"
+
+using namespace ctrk;
+
+struct ctr_fk_engine {
+    ctr_robot_desc desc;
+    KRobot         rb;
+    int            key;
+    int            device;
+    int            njv;
+    int            ntubes;
+    int            sm_count;
+    static constexpr int kStreams = 3;
+    cudaStream_t   streams[kStreams];
+    std::mutex     host_mu;      // serialises ctr_fk_batch_host / ctr_fk_single calls on one handle
+    char*          single_buf;   // device scratch of ctr_fk_single (lazily allocated)
+};
+
+namespace {
+
+// configurations below this count are not worth three extra launches for binning
+constexpr int64_t kMinBinBatch = 8192;
+// host-pointer path: configurations per pipelined chunk
+constexpr int64_t kHostChunk = 131072;
+
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int cuda_fail(const char* what, cudaError_t e)
+{
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+int check_common(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples)
+{
+    if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
+    if (B < 0 || B > 2147483647ll) { set_error("batch size %lld out of range [0, 2^31)", (long long)B); return CTR_FK_E_ARG; }
+    if (B > 0 && !jv) { set_error("null joint-value pointer"); return CTR_FK_E_NULL; }
+    if (mode == CTR_FK_MODE_STEP) {
+        if (!(step > 0.0) || !std::isfinite(step)) { set_error("arc-length step must be finite and > 0"); return CTR_FK_E_ARG; }
+    } else if (mode == CTR_FK_MODE_NSAMPLE) {
+        if (nsamples < 1) { set_error("nsamples must be >= 1"); return CTR_FK_E_ARG; }
+    } else {
+        set_error("unknown mode %d", mode);
+        return CTR_FK_E_ARG;
+    }
+    return 0;
+}
+
+// Build `order` (longest sweeps first) for a step-mode batch.  Stream-ordered allocations only.
+cudaError_t make_order(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t ns,
+                       int32_t** order_out, cudaStream_t st)
+{
+    const int nbins = h->rb.maxs + 2;
+    int32_t*  n = nullptr;
+    int32_t*  order = nullptr;
+    uint32_t* hist = nullptr;
+    cudaError_t e;
+    if ((e = cudaMallocAsync((void**)&n, sizeof(int32_t) * (size_t)B, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync((void**)&order, sizeof(int32_t) * (size_t)B, st)) != cudaSuccess) { cudaFreeAsync(n, st); return e; }
+    if ((e = cudaMallocAsync((void**)&hist, sizeof(uint32_t) * (size_t)nbins, st)) != cudaSuccess) { cudaFreeAsync(n, st); cudaFreeAsync(order, st); return e; }
+    e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)nbins, st);
+    if (e == cudaSuccess) e = launch_count_samples(h->key, h->rb, jv, B, mode, step, ns, n, hist, st);
+    if (e == cudaSuccess) e = launch_bin_offsets(hist, nbins, st);
+    if (e == cudaSuccess) e = launch_bin_scatter(n, B, hist, order, st);
+    cudaFreeAsync(n, st);
+    cudaFreeAsync(hist, st);
+    if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
+    *order_out = order;
+    return cudaSuccess;
+}
+
+int run_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+              uint32_t flags, double* tip, double* backbone, double* radius, int32_t* n_out,
+              double* step_out, double* alpha_base, int32_t* status, cudaStream_t st)
+{
+    if (B == 0) return 0;
+    FkArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.jv = jv; a.B = B; a.mode = mode; a.step = step; a.nsamples = nsamples;
+    a.tip = tip; a.n_out = n_out; a.step_out = step_out; a.alpha_base = alpha_base; a.status = status;
+    a.backbone = backbone; a.radius = radius; a.soa = (flags & CTR_FK_FLAG_SOA) ? 1 : 0;
+
+    int32_t* order = nullptr;
+    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch) {
+        cudaError_t e = make_order(h, jv, B, mode, step, nsamples, &order, st);
+        if (e != cudaSuccess) return cuda_fail("step-mode binning", e);
+        a.order = order;
+    }
+    const bool strict = (flags & CTR_FK_FLAG_STRICT) != 0;
+    cudaError_t e;
+    if (backbone) e = strict ? launch_backbone_strict(h->key, h->rb, a, st) : launch_backbone_fast(h->key, h->rb, a, st);
+    else          e = strict ? launch_tip_strict(h->key, h->rb, a, st) : launch_tip_fast(h->key, h->rb, a, st);
+    if (order) cudaFreeAsync(order, st);
+    if (e != cudaSuccess) return cuda_fail("solver kernel launch", e);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
+{
+    if (!desc || !out) { set_error("ctr_fk_create: null argument"); return CTR_FK_E_NULL; }
+    *out = nullptr;
+    KRobot rb;
+    int rc = make_krobot(desc, &rb);
+    if (rc) { set_error("ctr_fk_create: invalid robot descriptor (code %d)", rc); return rc; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_create: no usable CUDA device (this library has no CPU path)", e);
+    if (device < 0 || device >= ndev) { set_error("ctr_fk_create: device %d out of range (%d visible)", device, ndev); return CTR_FK_E_ARG; }
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return cuda_fail("ctr_fk_create: cudaSetDevice", g.err);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        set_error("ctr_fk_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return (int)cudaErrorNoKernelImageForDevice;
+    }
+    ctr_fk_engine* h = new (std::nothrow) ctr_fk_engine;
+    if (!h) { set_error("out of host memory"); return CTR_FK_E_NOMEM; }
+    h->desc = *desc;
+    h->rb = rb;
+    h->key = layout_key(desc);
+    h->device = device;
+    h->ntubes = desc_ntubes(desc);
+    h->njv = 1 + desc->nsections + h->ntubes;
+    h->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < ctr_fk_engine::kStreams; ++i) h->streams[i] = nullptr;
+    h->single_buf = nullptr;
+    for (int i = 0; i < ctr_fk_engine::kStreams; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
+            for (int j = 0; j < i; ++j) cudaStreamDestroy(h->streams[j]);
+            delete h;
+            return cuda_fail("cudaStreamCreate", e);
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+int ctr_fk_destroy(ctr_fk_handle h)
+{
+    if (!h) return 0;
+    {
+        DeviceGuard g(h->device);
+        for (int i = 0; i < ctr_fk_engine::kStreams; ++i)
+            if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
+        if (h->single_buf) cudaFree(h->single_buf);
+    }
+    delete h;
+    return 0;
+}
+
+int ctr_fk_get_desc(ctr_fk_handle h, ctr_robot_desc* out)
+{
+    if (!h || !out) { set_error("ctr_fk_get_desc: null argument"); return CTR_FK_E_NULL; }
+    *out = h->desc;
+    return 0;
+}
+
+int ctr_fk_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                 uint32_t flags, double* tip, double* backbone, double* radius, int32_t* n_out,
+                 double* step_out, double* alpha_base, int32_t* status, void* stream)
+{
+    int rc = check_common(h, jv, B, mode, step, nsamples);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    return run_batch(h, jv, B, mode, step, nsamples, flags, tip, backbone, radius, n_out, step_out,
+                     alpha_base, status, (cudaStream_t)stream);
+}
+
+int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                      uint32_t flags, double* tip, int32_t* n_out, double* step_out, int32_t* status)
+{
+    int rc = check_common(h, jv, B, mode, step, nsamples);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+
+    constexpr int NS = ctr_fk_engine::kStreams;
+    const int64_t chunk = std::min<int64_t>(kHostChunk, B);
+    const int njv = h->njv;
+    // one slab per stream: jv | tip | n_out | step_out | status
+    const size_t off_tip  = sizeof(double) * (size_t)chunk * njv;
+    const size_t off_n    = off_tip + sizeof(double) * (size_t)chunk * 12;
+    const size_t off_step = off_n + sizeof(int32_t) * (size_t)chunk * 2;       // keeps 8-B alignment
+    const size_t off_stat = off_step + sizeof(double) * (size_t)chunk;
+    const size_t slab     = ((off_stat + sizeof(int32_t) * (size_t)chunk * 2 + 255) / 256) * 256;
+    const int nslab = (int)std::min<int64_t>(NS, (B + chunk - 1) / chunk);
+    char* dbuf = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dbuf, slab * (size_t)nslab);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_batch_host: device staging allocation", e);
+
+    int ret = 0;
+    int64_t done = 0;
+    for (int c = 0; done < B && ret == 0; ++c, done += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, B - done);
+        cudaStream_t st = h->streams[c % NS];
+        char* base = dbuf + slab * (size_t)(c % nslab);
+        double*  d_jv   = (double*)base;
+        double*  d_tip  = tip ? (double*)(base + off_tip) : nullptr;
+        int32_t* d_n    = n_out ? (int32_t*)(base + off_n) : nullptr;
+        double*  d_step = step_out ? (double*)(base + off_step) : nullptr;
+        int32_t* d_stat = status ? (int32_t*)(base + off_stat) : nullptr;
+        // stream order protects slab reuse: chunk c and chunk c+nslab share a stream
+        if ((e = cudaMemcpyAsync(d_jv, jv + done * njv, sizeof(double) * (size_t)nb * njv, cudaMemcpyHostToDevice, st)) != cudaSuccess) { ret = cuda_fail("H2D copy", e); break; }
+        ret = run_batch(h, d_jv, nb, mode, step, nsamples, flags, d_tip, nullptr, nullptr, d_n, d_step, nullptr, d_stat, st);
+        if (ret) break;
+        if (tip && (e = cudaMemcpyAsync(tip + done * 12, d_tip, sizeof(double) * (size_t)nb * 12, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (n_out && (e = cudaMemcpyAsync(n_out + done, d_n, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (step_out && (e = cudaMemcpyAsync(step_out + done, d_step, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (status && (e = cudaMemcpyAsync(status + done, d_stat, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+    }
+    for (int i = 0; i < NS; ++i) {
+        e = cudaStreamSynchronize(h->streams[i]);
+        if (e != cudaSuccess && ret == 0) ret = cuda_fail("ctr_fk_batch_host: stream sync", e);
+    }
+    cudaFree(dbuf);
+    return ret;
+}
+
+int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int32_t nsamples, uint32_t flags,
+                  double* tip, double* backbone, double* radius, int32_t* n_out, double* step_out,
+                  double* alpha_base)
+{
+    int rc = check_common(h, jv, 1, mode, step, nsamples);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    const size_t maxs = (size_t)h->rb.maxs;
+    // layout (doubles): jv[16] | tip[12] | step[1] | alpha[8] | n,status (1 double) | radius[maxs] | backbone[12 maxs]
+    const size_t o_tip = 16, o_step = 28, o_al = 29, o_n = 37, o_rad = 38, o_bb = 38 + maxs;
+    const size_t total = (o_bb + 12 * maxs) * sizeof(double);
+    cudaError_t e;
+    if (!h->single_buf && (e = cudaMalloc((void**)&h->single_buf, total)) != cudaSuccess)
+        return cuda_fail("ctr_fk_single: scratch allocation", e);
+    double* d = (double*)h->single_buf;
+    cudaStream_t st = h->streams[0];
+    if ((e = cudaMemcpyAsync(d, jv, sizeof(double) * (size_t)h->njv, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail("H2D copy", e);
+    int32_t* d_n = (int32_t*)(d + o_n);
+    rc = run_batch(h, d, 1, mode, step, nsamples, flags, d + o_tip, (backbone || radius) ? d + o_bb : nullptr,
+                   radius ? d + o_rad : nullptr, d_n, d + o_step, d + o_al, d_n + 1, st);
+    if (rc) return rc;
+    double head[38];
+    if ((e = cudaMemcpyAsync(head, d, sizeof head, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail("D2H copy", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail("ctr_fk_single: sync", e);
+    int32_t nn[2];
+    std::memcpy(nn, head + o_n, sizeof nn);
+    if (tip) std::memcpy(tip, head + o_tip, 12 * sizeof(double));
+    if (step_out) *step_out = head[o_step];
+    if (alpha_base) std::memcpy(alpha_base, head + o_al, sizeof(double) * (size_t)h->ntubes);
+    if (n_out) *n_out = nn[0];
+    if (nn[0] > 0) {
+        if (radius && (e = cudaMemcpy(radius, d + o_rad, sizeof(double) * (size_t)nn[0], cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail("D2H copy", e);
+        if (backbone && (e = cudaMemcpy(backbone, d + o_bb, sizeof(double) * 12 * (size_t)nn[0], cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail("D2H copy", e);
+    }
+    return nn[1] ? CTR_FK_STATUS_PHI_RANGE : 0;
+}
+
+int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                     uint32_t flags, double* tip, int32_t* n_out, double* step_out, int32_t* status, void* stream)
+{
+    int rc = check_common(h, jv, B, mode, step, nsamples);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    FkArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.jv = jv; a.B = B; a.mode = mode; a.step = step; a.nsamples = nsamples;
+    a.tip = tip; a.n_out = n_out; a.step_out = step_out; a.status = status;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* order = nullptr;
+    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch) {
+        cudaError_t e = make_order(h, jv, B, mode, step, nsamples, &order, st);
+        if (e != cudaSuccess) return cuda_fail("step-mode binning", e);
+        a.order = order;
+    }
+    cudaError_t e = launch_tip_f32(h->key, h->rb, a, st);
+    if (order) cudaFreeAsync(order, st);
+    if (e != cudaSuccess) return cuda_fail("f32 solver kernel launch", e);
+    return 0;
+}
+
+int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples, double fd_trans,
+                          double fd_rot, double* jac, double* tip, void* stream)
+{
+    int rc = check_common(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples);
+    if (rc) return rc;
+    if (!jac && B > 0) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
+    if (!(fd_trans != 0.0) || !(fd_rot != 0.0) || !std::isfinite(fd_trans) || !std::isfinite(fd_rot)) {
+        set_error("finite-difference steps must be finite and non-zero");
+        return CTR_FK_E_ARG;
+    }
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    JacArgs a;
+    a.jv = jv; a.B = B; a.nsamples = nsamples; a.fd_trans = fd_trans; a.fd_rot = fd_rot; a.jac = jac; a.tip = tip;
+    cudaError_t e = launch_jacobian(h->key, h->rb, a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail("jacobian kernel launch", e);
+    return 0;
+}
+
+int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples, double fd_trans,
+                         double fd_rot, double* jac, double* tip)
+{
+    int rc = check_common(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!jac) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    const size_t njv = (size_t)h->njv;
+    const size_t b_jv = sizeof(double) * njv * (size_t)B, b_jac = sizeof(double) * 6 * njv * (size_t)B, b_tip = sizeof(double) * 12 * (size_t)B;
+    char* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, b_jv + b_jac + b_tip);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: allocation", e);
+    cudaStream_t st = h->streams[0];
+    double* d_jv = (double*)d;
+    double* d_jac = (double*)(d + b_jv);
+    double* d_tip = (double*)(d + b_jv + b_jac);
+    e = cudaMemcpyAsync(d_jv, jv, b_jv, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = ctr_fk_jacobian_batch(h, d_jv, B, nsamples, fd_trans, fd_rot, d_jac, tip ? d_tip : nullptr, st);
+        if (rc == 0) {
+            e = cudaMemcpyAsync(jac, d_jac, b_jac, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && tip) e = cudaMemcpyAsync(tip, d_tip, b_tip, cudaMemcpyDeviceToHost, st);
+        }
+    }
+    cudaError_t es = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: copy", e);
+    if (es != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: sync", es);
+    return 0;
+}
+
+int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B, double* jv, void* stream)
+{
+    if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
+    if (B < 0 || first_config < 0) { set_error("negative batch size or offset"); return CTR_FK_E_ARG; }
+    if (B == 0) return 0;
+    if (!jv) { set_error("null joint-value pointer"); return CTR_FK_E_NULL; }
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    SamplerTable tb;
+    make_sampler_table(&h->desc, &tb);
+    SamplerArgs a;
+    a.seed = seed; a.first = first_config; a.B = B; a.njv = tb.njv; a.jv = jv;
+    for (int j = 0; j < 16; ++j) a.scale[j] = j < tb.njv ? tb.scale[j] : 0.0;
+    cudaError_t e = launch_sampler(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail("sampler kernel launch", e);
+    return 0;
+}
+
+int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* stream)
+{
+    if (iters < 1) { set_error("iters must be >= 1"); return CTR_FK_E_ARG; }
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return cuda_fail("cudaDeviceGetAttribute", e);
+    static double* sink = nullptr;   // one 8-byte device word per process; never written
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!sink && (e = cudaMalloc((void**)&sink, sizeof(double))) != cudaSuccess) return cuda_fail("cudaMalloc", e);
+    }
+    const int blocks = sms * 8;
+    e = launch_fp64_probe(iters, blocks, sink, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail("probe kernel launch", e);
+    if (flops_issued)
+        *flops_issued = 2.0 * (double)blocks * kProbeThreads * kProbeChains * 8.0 * (double)iters;
+    return 0;
+}
+
+}  // extern "C"

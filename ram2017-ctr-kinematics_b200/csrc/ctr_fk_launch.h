@@ -1,0 +1,78 @@
+// ctr_fk_launch.h — launcher interface between the C-ABI layer (ctr_fk_api.cu) and the kernel
+// translation units.  Kernels are instantiated per section layout (14 layouts: 1-3 sections of
+// 1 or 2 tubes) and selected by ctrk::layout_key().
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ctr_fk_core.cuh"
+
+namespace ctrk {
+
+struct FkArgs {
+    const double*  jv;          // [B][NJ]
+    int64_t        B;
+    int            mode;        // CTR_FK_MODE_*
+    double         step;
+    int            nsamples;
+    const int32_t* order;       // nullable: order[i] = configuration solved by thread i
+    double*        tip;         // [B][12]            nullable
+    int32_t*       n_out;       // [B]                nullable
+    double*        step_out;    // [B]                nullable
+    double*        alpha_base;  // [B][T]             nullable
+    int32_t*       status;      // [B]                nullable
+    double*        backbone;    // [B][maxs][12] or [maxs][12][B]   nullable
+    double*        radius;      // [B][maxs]     or [maxs][B]       nullable
+    int            soa;         // backbone/radius layout
+};
+
+struct JacArgs {
+    const double* jv;
+    int64_t       B;
+    int           nsamples;
+    double        fd_trans, fd_rot;
+    double*       jac;          // [B][NJ][6]
+    double*       tip;          // [B][12] nullable
+};
+
+constexpr int kBlock = 128;     // threads per CTA for every solver kernel
+
+// tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
+cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+cudaError_t launch_tip_strict(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+cudaError_t launch_tip_f32(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+// backbone solvers (two passes inside one kernel; the output buffer doubles as scratch)
+cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+// finite-difference Jacobian (fast arithmetic)
+cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);
+
+// step-mode binning: sample count per configuration + histogram, then a counting sort that
+// yields `order` with the longest sweeps first (ctr_fk_kernels_util.cu)
+cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, int64_t B, int mode,
+                                 double step, int nsamples, int32_t* n, uint32_t* hist, cudaStream_t st);
+cudaError_t launch_bin_offsets(uint32_t* hist, int nbins, cudaStream_t st);   // in place: descending exclusive scan
+cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, cudaStream_t st);
+
+struct SamplerArgs {
+    uint64_t seed;
+    int64_t  first;
+    int64_t  B;
+    int      njv;
+    double   scale[16];
+    double*  jv;
+};
+cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
+cudaError_t launch_fp64_probe(int iters, int blocks, double* sink, cudaStream_t st);
+constexpr int kProbeThreads = 256;
+constexpr int kProbeChains  = 8;
+
+}  // namespace ctrk
+
+// all section layouts: (sections, tubes in section 0, 1, 2)
+#define CTRK_FOR_EACH_LAYOUT_K(X) \
+    X(1, 1, 0, 0) X(1, 2, 0, 0) \
+    X(2, 1, 1, 0) X(2, 1, 2, 0) X(2, 2, 1, 0) X(2, 2, 2, 0) \
+    X(3, 1, 1, 1) X(3, 1, 1, 2) X(3, 1, 2, 1) X(3, 1, 2, 2) \
+    X(3, 2, 1, 1) X(3, 2, 1, 2) X(3, 2, 2, 1) X(3, 2, 2, 2)

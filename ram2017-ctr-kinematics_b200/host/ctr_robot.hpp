@@ -1,0 +1,122 @@
+// ctr_robot.hpp — C++14 host object with the shape of the reference's CTR::Robot<double>
+// (ctr_source/ctr_robot.h:76-173), implemented over the C ABI of include/ctr_fk.h.
+// Same method names, argument meaning and error behaviour for the forward-kinematics path:
+//   - construction from a ctr_resources XML file runs one FK at the XML's phi values
+//     (ctr_static.h:248-252);
+//   - a robot that failed to construct answers Identity / 0 / false ("FOOL: no robot",
+//     ctr_robot.cpp:96-106) instead of throwing;
+//   - calcKinematic keeps the last result, read back with getNSamples / getTransformSample /
+//     getRadiusSample / getTip* (robot_i.h:520-533).
+// New: calcKinematicBatch, the batched solve this engine exists for.  Every solve — single or
+// batched — runs on the GPU; there is no CPU implementation behind this class.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <iosfwd>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "ctr_fk.h"
+
+namespace ctrb200 {
+
+struct Vector3 {
+    double v[3];
+    double x() const { return v[0]; }
+    double y() const { return v[1]; }
+    double z() const { return v[2]; }
+};
+
+// 3x4 rigid transform, column-major like Erl::Transform::getData(.., ColMajor).
+struct Transform {
+    double m[12];
+    static Transform Identity();
+    double operator()(int r, int c) const { return m[3 * c + r]; }
+    Vector3 getTranslation() const { return Vector3{{m[9], m[10], m[11]}}; }
+    void getData(double* out) const { for (int i = 0; i < 12; ++i) out[i] = m[i]; }
+    Transform operator*(const Transform& b) const;
+};
+
+typedef std::vector<double> VectorJ;
+// 6 x n_jv, column-major (Eigen::Matrix<Real,6,Dynamic,ColMajor>, ctr_robot.h:91)
+struct MatJacobian {
+    int cols = 0;
+    std::vector<double> data;
+    double operator()(int r, int c) const { return data[6 * c + r]; }
+};
+
+typedef std::mt19937 CT_RNG;                                   // _forwards.h:62-66
+typedef std::uniform_real_distribution<double> CT_RND;
+
+class Robot {
+public:
+    Robot();
+    Robot(const Robot& other);
+    // sections in base-to-tip order; init is orthogonalised like the XML path
+    Robot(std::size_t maxSample, const Transform& initTrafo, const std::vector<ctr_section_desc>& sections,
+          int device = 0);
+    Robot(std::size_t maxSample, const std::string& xmlFilename, int device = 0);
+    ~Robot();
+    Robot& operator=(const Robot& other);
+
+    bool init() const { return engine_ != nullptr; }
+    explicit operator bool() const { return init(); }
+
+    // ctr_robot.h:111-117
+    Transform calcKinematic(const VectorJ& jv, const double& arcLengthStep);
+    Transform calcKinematic(const VectorJ& jv, const double& arcLengthStep, double& arcLengthStepReturn);
+    Transform calcKinematic(const VectorJ& jv, const std::size_t& nSamples);
+    Transform calcKinematic(const VectorJ& jv, const std::size_t& nSamples, double& arcLengthStepReturn);
+    void      calcKinematic(double* const jv, const double& arcLengthStep, double* tr);
+
+    // Batched solve, HOST pointers: jv [B][n_jv] in, tip [B][12] out (column-major 3x4 each);
+    // n_out / step_out / status nullable.  Returns the C-ABI code (0 = OK).
+    int calcKinematicBatch(const double* jv, std::int64_t B, const double& arcLengthStep, double* tip,
+                           std::int32_t* nOut = nullptr, double* stepOut = nullptr, std::int32_t* status = nullptr);
+    int calcKinematicBatch(const double* jv, std::int64_t B, const std::size_t& nSamples, double* tip,
+                           std::int32_t* nOut = nullptr, double* stepOut = nullptr, std::int32_t* status = nullptr);
+
+    // ctr_robot.h:122 (NSamples form, tip only)
+    void calcJacobian(const VectorJ& jv, const std::size_t& nSamples, const double& fdTrans, const double& fdRot,
+                      MatJacobian& jacobianTip);
+
+    std::size_t getNSections() const;
+    std::size_t getNTubes() const;
+    std::size_t getNJointValues() const;
+    double      getMaxLength() const noexcept;
+    std::size_t getMaxSamples() const noexcept;
+    std::size_t getNSamples() const noexcept { return nsamples_; }
+    double      getRadiusSample(unsigned s) const noexcept;
+    Transform   getTransformSample(unsigned s) const noexcept;
+    Vector3     getTranslationSample(unsigned s) const noexcept;
+    double      getTipRadius() const noexcept;
+    Transform   getTipTransform() const noexcept;
+    Vector3     getTipTranslation() const noexcept;
+    VectorJ     getJointValues() const noexcept { return last_jv_; }
+    const std::vector<double>& getBaseAngles() const noexcept { return alpha_base_; }
+    bool        getSection(unsigned i, ctr_section_desc* out) const noexcept;
+    const ctr_robot_desc& descriptor() const { return desc_; }
+    ctr_fk_handle handle() const { return engine_; }
+
+    void getRandomJointValues(CT_RNG& rng, CT_RND& rnd, VectorJ& jvReturn) const;   // robot_i.h:1308-1317
+
+    friend std::ostream& operator<<(std::ostream& os, const Robot& r);
+
+private:
+    void build(int device);
+    void destroy();
+    Transform solve_single(const double* jv, int mode, double step, std::size_t ns, double* stepReturn);
+
+    ctr_robot_desc desc_;
+    ctr_fk_handle  engine_;
+    int            device_;
+    std::size_t    nsamples_;
+    std::vector<double> frames_;      // [max_samples][12]
+    std::vector<double> radius_;      // [max_samples]
+    std::vector<double> alpha_base_;
+    VectorJ             last_jv_;
+};
+
+}  // namespace ctrb200

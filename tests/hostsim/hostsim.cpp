@@ -1,0 +1,69 @@
+// hostsim.cpp — TEST HARNESS ONLY.  Compiles the kernels' per-configuration solvers
+// (ram2017-ctr-kinematics_b200/csrc/ctr_fk_core.cuh, the code each GPU thread runs) for the CPU
+// so that their logic can be compared with the oracle in a container without a GPU.  Not part of
+// the product: libctrfk.so has no CPU path and never links this file.
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/ctr_fk.h"
+#include "../../ram2017-ctr-kinematics_b200/csrc/ctr_fk_krobot.h"
+
+using namespace ctrk;
+
+namespace {
+struct Park {
+    double* base;   // [maxs][4]
+    void operator()(int k, double ux, double uy, double uz, double al) const
+    {
+        if (!base) return;
+        base[4 * k] = ux; base[4 * k + 1] = uy; base[4 * k + 2] = uz; base[4 * k + 3] = al;
+    }
+};
+
+template <class L>
+void run(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, int fast, double* tip,
+         int32_t* n_out, double* step_out, double* alpha_base, double* samples)
+{
+    for (int64_t i = 0; i < B; ++i) {
+        Ctl<L> c;
+        setup_control<L>(rb, jv + i * L::NJ, mode, step, ns, c);
+        if (n_out) n_out[i] = c.nframes;
+        if (step_out) step_out[i] = c.h;
+        if (c.status) continue;
+        Park park{samples ? samples + i * 4 * (int64_t)rb.maxs : nullptr};
+        double t[12], ab[L::T];
+        if (fast) solve_fast<L>(rb, c, t, ab, park);
+        else      solve_strict<L, true>(rb, c, t, ab, park);
+        if (tip) std::memcpy(tip + 12 * i, t, sizeof t);
+        if (alpha_base) std::memcpy(alpha_base + L::T * i, ab, sizeof ab);
+    }
+}
+}  // namespace
+
+extern "C" int hostsim_fk(const ctr_robot_desc* d, const double* jv, int64_t B, int mode, double step, int ns,
+                          int fast, double* tip, int32_t* n_out, double* step_out, double* alpha_base,
+                          double* samples)
+{
+    KRobot rb;
+    int rc = make_krobot(d, &rb);
+    if (rc) return rc;
+    switch (layout_key(d)) {
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: run<Lay<S, A, Bq, C>>(rb, jv, B, mode, step, ns, fast, tip, n_out, step_out, alpha_base, samples); break;
+        CTRK_FOR_EACH_LAYOUT(X)
+#undef X
+        default: return CTR_FK_E_DESC;
+    }
+    return 0;
+}
+
+extern "C" void hostsim_sincos(const double* x, int64_t n, double* s, double* c)
+{
+    for (int64_t i = 0; i < n; ++i) fast_sincos(x[i], s[i], c[i]);
+}
+
+// SE(3) step: strict 3x4 (column-major) and fast (quaternion w,x,y,z + translation)
+extern "C" void hostsim_se3(double ux, double uy, double uz, double h, double* strict12, double* fast7)
+{
+    tf_step_strict(ux, uy, uz, h, 1e-12, strict12);
+    se3_step_fast(ux, uy, uz, h, 1e-12, fast7[0], fast7[1], fast7[2], fast7[3], fast7[4], fast7[5], fast7[6]);
+}

@@ -1,0 +1,329 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/ctr_fk.h), against
+the CPU oracle on the same seeded inputs.  Gate (BASELINE.json north_star): tip position within
+1e-9 m, orientation within 1e-9 rad, sample count and returned step exactly equal."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def engines(ctrfk, robots, dev):
+    e = {n: ctrfk.Engine(d, 0) for n, d in robots.items()}
+    yield e
+    for x in e.values():
+        x.close()
+
+
+def run_gpu(ctrfk, eng, jv_np, mode, flags=0, backbone=False, radius=False, soa=False, **kw):
+    B = jv_np.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    jv = torch.from_numpy(np.ascontiguousarray(jv_np)).cuda()
+    maxs = eng.desc.max_samples
+    out = dict(tip=torch.full((B, 12), -7.0, dtype=torch.float64, device="cuda"),
+               n=torch.full((B,), -7, dtype=torch.int32, device="cuda"),
+               step=torch.full((B,), -7.0, dtype=torch.float64, device="cuda"),
+               alpha_base=torch.full((B, eng.ntubes), -7.0, dtype=torch.float64, device="cuda"),
+               status=torch.full((B,), -7, dtype=torch.int32, device="cuda"))
+    bb = torch.zeros((maxs, 12, B) if soa else (B, maxs, 12), dtype=torch.float64, device="cuda") if backbone else None
+    rd = torch.zeros((maxs, B) if soa else (B, maxs), dtype=torch.float64, device="cuda") if radius else None
+    if soa:
+        flags |= ctrfk.FLAG_SOA
+    before = ctrfk.launch_count()
+    eng.batch(jv, B, mode, flags=flags, tip=out["tip"], backbone=bb, radius=rd, n_out=out["n"],
+              step_out=out["step"], alpha_base=out["alpha_base"], status=out["status"], stream=st, **kw)
+    torch.cuda.synchronize()
+    assert B == 0 or ctrfk.launch_count() > before, "no kernel of libctrfk.so was launched"
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    if backbone:
+        res["backbone"] = (bb.permute(2, 0, 1) if soa else bb).cpu().numpy()
+    if radius:
+        res["radius"] = (rd.permute(1, 0) if soa else rd).cpu().numpy()
+    return res
+
+
+def assert_parity(o, g, tol_pos=util.TOL_POS, tol_rot=util.TOL_ROT):
+    assert np.array_equal(o["n"], g["n"])
+    assert np.array_equal(o["step"], g["step"], equal_nan=True)
+    ok = o["status"] == 0
+    assert np.array_equal(o["status"], g["status"])
+    dp, ang = util.pose_errors(o["tip"][ok], g["tip"][ok])
+    assert dp.max() <= tol_pos, dp.max()
+    assert ang.max() <= tol_rot, ang.max()
+    assert np.abs(o["alpha_base"][ok] - g["alpha_base"][ok]).max() <= 1e-9
+    assert np.isnan(g["tip"][~ok]).all()
+    return dp.max(), ang.max()
+
+
+MODES = [("F256", 1, dict(nsamples=256)), ("S256", 0, None)]
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+@pytest.mark.parametrize("flags", [0, 1], ids=["fast", "strict"])
+def test_tip_parity_100k(ctrfk, oracle, robots, engines, name, flags):
+    d = robots[name]
+    B = 100_000
+    jv = ctrfk.sample_joints_host(d, util.SEEDS[name], 0, B)
+    for tag, mode, kw in MODES:
+        kw = kw or dict(step=d.max_length / 256.0)
+        o = oracle.fk_batch(d, jv, mode, **kw)
+        g = run_gpu(ctrfk, engines[name], jv, mode, flags=flags, **kw)
+        dp, ang = assert_parity(o, g)
+        # measured margins are recorded in DESIGN.md; both variants sit far inside the gate
+        assert dp < (1e-10 if flags == 0 else 1e-12) and ang < 1e-10, (tag, dp, ang)
+
+
+def test_golden_vectors(ctrfk, robots, engines):
+    g = np.load(os.path.join(HERE, "golden", "oracle_golden.npz"))
+    for name in util.ROBOT_FILES:
+        key = name.replace(".xml", "")
+        d = robots[name]
+        jv = g[key + "/jv"]
+        for tag, mode in (("F", 1), ("S", 0)):
+            r = run_gpu(ctrfk, engines[name], jv, mode, step=d.max_length / 256.0, nsamples=256)
+            assert np.array_equal(r["n"], g["%s/%s/n" % (key, tag)])
+            assert np.array_equal(r["step"], g["%s/%s/step" % (key, tag)])
+            dp, ang = util.pose_errors(r["tip"], g["%s/%s/tip" % (key, tag)])
+            assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+            assert np.abs(r["alpha_base"] - g["%s/%s/alpha_base" % (key, tag)]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_edge_cases(ctrfk, oracle, robots, engines, name):
+    d = robots[name]
+    jv = util.edge_joint_sets(d)
+    bad = jv[:3].copy()
+    bad[0, 1] = -1e-6                       # phi < 0
+    bad[1, 1] = d.sec[0].length * 1.0001    # phi > Length
+    bad[2, 1] = np.nan
+    jv = np.vstack([jv, bad])
+    for mode, kw in ((1, dict(nsamples=256)), (1, dict(nsamples=1)), (1, dict(nsamples=5)), (1, dict(nsamples=1000)),
+                     (0, dict(step=d.max_length / 256.0)), (0, dict(step=0.01)), (0, dict(step=1.0)),
+                     (0, dict(step=2e-5))):
+        o = oracle.fk_batch(d, jv, mode, **kw)
+        for flags in (0, 1):
+            g = run_gpu(ctrfk, engines[name], jv, mode, flags=flags, **kw)
+            assert_parity(o, g)
+            assert list(g["status"][-3:]) == [1, 1, 1] and (g["n"][-3:] == 0).all()
+
+
+def test_empty_single_and_ragged_batches(ctrfk, oracle, robots, engines):
+    name = "ctr_sec2_tub3.xml"
+    d = robots[name]
+    for B in (0, 1, 31, 127, 128, 129, 1000):
+        jv = ctrfk.sample_joints_host(d, 5, 0, B)
+        g = run_gpu(ctrfk, engines[name], jv, 1, nsamples=64)
+        if B:
+            o = oracle.fk_batch(d, jv, 1, nsamples=64)
+            assert_parity(o, g)
+
+
+def test_bad_arguments_are_rejected(ctrfk, robots, engines):
+    eng = engines["ctr_sec2_tub3.xml"]
+    jv = torch.zeros(4, 6, dtype=torch.float64, device="cuda")
+    for kw in (dict(mode=0, step=0.0), dict(mode=0, step=-1.0), dict(mode=0, step=float("nan")),
+               dict(mode=1, nsamples=0), dict(mode=7, step=1e-3)):
+        mode = kw.pop("mode")
+        with pytest.raises(ctrfk.CtrFkError) as ei:
+            eng.batch(jv, 4, mode, **kw)
+        assert ei.value.code == ctrfk.E_ARG
+    with pytest.raises(ctrfk.CtrFkError) as ei:
+        eng.batch(None, 4, 1, nsamples=4)
+    assert ei.value.code == ctrfk.E_NULL
+
+
+def test_step_mode_binning_does_not_change_results(ctrfk, oracle, robots, engines):
+    """Configurations are counting-sorted by sample count for the launch only: outputs land at
+    their original index and are bit-identical with and without binning."""
+    name = "ctr_sec3_tub4.xml"
+    d = robots[name]
+    jv = ctrfk.sample_joints_host(d, 77, 0, 50_000)
+    step = d.max_length / 256.0
+    a = run_gpu(ctrfk, engines[name], jv, 0, step=step)
+    b = run_gpu(ctrfk, engines[name], jv, 0, step=step, flags=ctrfk.FLAG_NO_BINNING)
+    for k in ("tip", "n", "step", "alpha_base", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    o = oracle.fk_batch(d, jv, 0, step=step)
+    assert_parity(o, a)
+
+
+def test_step_mode_dropped_tip_sample(ctrfk, oracle, robots, dev):
+    d = ctrfk.RobotDesc.from_buffer_copy(robots["ctr_sec3_tub4.xml"])
+    d.max_samples = 64
+    eng = ctrfk.Engine(d, 0)
+    jv = ctrfk.sample_joints_host(d, 1234, 0, 20_000)
+    step = d.max_length / 64.0
+    o = oracle.fk_batch(d, jv, 0, step=step)
+    arc = jv[:, 1] + jv[:, 4] + jv[:, 6]
+    assert (o["n"] == np.maximum(1, np.floor(arc / step)) - 1).sum() > 10      # the quirk occurs
+    for flags in (0, 1):
+        g = run_gpu(ctrfk, eng, jv, 0, step=step, flags=flags)
+        assert_parity(o, g)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["ctr_sec3_tub4.xml", "ctr_sec2_tub3.xml"])
+@pytest.mark.parametrize("soa", [False, True], ids=["aos", "soa"])
+def test_backbone_and_radius_parity(ctrfk, oracle, robots, engines, name, soa):
+    d = robots[name]
+    B = 3000
+    jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name], 0, B), util.edge_joint_sets(d)])
+    for mode, kw in ((1, dict(nsamples=256)), (0, dict(step=d.max_length / 256.0)), (1, dict(nsamples=3))):
+        o = oracle.fk_batch(d, jv, mode, backbone=True, radius=True, **kw)
+        for flags in (0, 1):
+            g = run_gpu(ctrfk, engines[name], jv, mode, flags=flags, backbone=True, radius=True, soa=soa, **kw)
+            assert_parity(o, g)
+            for i in range(0, jv.shape[0], 37):
+                n = o["n"][i]
+                dp, ang = util.pose_errors(o["backbone"][i, :n], g["backbone"][i, :n])
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+                assert np.array_equal(o["radius"][i, :n], g["radius"][i, :n])
+                # the tip output is the last frame of the backbone
+                assert np.array_equal(g["backbone"][i, n - 1], g["tip"][i])
+
+
+def test_host_pointer_batch_and_single(ctrfk, oracle, robots, engines):
+    name = "ctr_sec3_tub5.xml"
+    d = robots[name]
+    eng = engines[name]
+    B = 300_000                                     # > 2 chunks of the pipelined host path
+    jv = ctrfk.sample_joints_host(d, util.SEEDS[name], 0, B)
+    tip = np.zeros((B, 12)); n = np.zeros(B, np.int32); st = np.zeros(B); status = np.zeros(B, np.int32)
+    eng.batch_host(jv, B, 1, nsamples=128, tip=tip, n_out=n, step_out=st, status=status)
+    g = run_gpu(ctrfk, eng, jv, 1, nsamples=128)
+    assert np.array_equal(tip, g["tip"]) and np.array_equal(n, g["n"]) and np.array_equal(st, g["step"])
+    # pinned memory gives the same answer
+    jvp = torch.from_numpy(jv).pin_memory(); tipp = torch.zeros(B, 12, dtype=torch.float64).pin_memory()
+    eng.batch_host(jvp, B, 1, nsamples=128, tip=tipp)
+    assert np.array_equal(tipp.numpy(), tip)
+    o = oracle.fk_batch(d, jv[:20000], 1, nsamples=128)
+    dp, ang = util.pose_errors(o["tip"], tip[:20000])
+    assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+    # single configuration through the same kernels (the reference's one-shot call)
+    maxs = d.max_samples
+    for q in jv[:5]:
+        t1 = np.zeros(12); bb = np.zeros((maxs, 12)); rd = np.zeros(maxs); ab = np.zeros(d.ntubes)
+        import ctypes as C
+        nn = C.c_int32(0); hh = C.c_double(0)
+        rc = eng.single(q, 0, step=d.max_length / 256.0, tip=t1, backbone=bb, radius=rd,
+                        n_out=C.addressof(nn), step_out=C.addressof(hh), alpha_base=ab)
+        assert rc == 0
+        r = oracle.fk_one(d, q, 0, step=d.max_length / 256.0)
+        assert nn.value == r["n"] and hh.value == r["step"]
+        dp, ang = util.pose_errors(r["backbone"], bb[: r["n"]])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+        assert np.array_equal(rd[: r["n"]], r["radius"])
+        assert np.abs(ab - r["alpha_base"]).max() < 1e-9
+        assert np.array_equal(t1, bb[r["n"] - 1])
+
+
+def test_device_sampler_equals_host_sampler(ctrfk, robots, engines):
+    for name in util.ROBOT_FILES:
+        d = robots[name]
+        B = 10_000
+        jv = torch.empty(B, d.njoints, dtype=torch.float64, device="cuda")
+        engines[name].sample_joints(util.SEEDS[name], 12345, B, jv, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(jv.cpu().numpy(), ctrfk.sample_joints_host(d, util.SEEDS[name], 12345, B))
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_jacobian_parity(ctrfk, oracle, robots, engines, name):
+    d = robots[name]
+    B = 200
+    jv = ctrfk.sample_joints_host(d, 9, 0, B)
+    jv[0, 1] = d.sec[0].length - 1e-7            # forces the backward difference (robot_i.h:948-950)
+    fd_t, fd_r = 1e-5, 1e-4
+    jac = np.zeros((B, d.njoints, 6)); tip = np.zeros((B, 12))
+    engines[name].jacobian_host(jv, B, 128, fd_t, fd_r, jac, tip)
+    for i in range(0, B, 7):
+        J, t = oracle.jacobian(d, jv[i], 128, fd_t, fd_r)
+        dp, ang = util.pose_errors(t[None], tip[i][None])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+        # finite differences divide the 1e-13-level arithmetic differences by the step
+        assert np.abs(J - jac[i]).max() < 1e-6, np.abs(J - jac[i]).max()
+        assert np.all(jac[i][2] == 0.0)
+
+
+# ---- full-size, size-independent properties (BASELINE.json config 2: 1M configurations) --------
+
+def rz_batch(theta):
+    c, s = np.cos(theta), np.sin(theta)
+    R = np.zeros((theta.size, 3, 3))
+    R[:, 0, 0] = c; R[:, 0, 1] = -s; R[:, 1, 0] = s; R[:, 1, 1] = c; R[:, 2, 2] = 1
+    return R
+
+
+def test_full_size_properties_1M(ctrfk, oracle, robots, engines):
+    name = "ctr_sec2_tub3.xml"
+    d = robots[name]
+    eng = engines[name]
+    B = 1_000_000
+    st = torch.cuda.current_stream().cuda_stream
+    jv = torch.empty(B, d.njoints, dtype=torch.float64, device="cuda")
+    eng.sample_joints(util.SEEDS[name], 0, B, jv, st)
+    tip = torch.empty(B, 12, dtype=torch.float64, device="cuda")
+    tip2 = torch.empty_like(tip)
+    eng.batch(jv, B, 1, nsamples=256, tip=tip, stream=st)
+    eng.batch(jv, B, 1, nsamples=256, tip=tip2, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(tip, tip2)                                    # deterministic
+    T = tip.cpu().numpy()
+    assert np.isfinite(T).all()
+    R = T[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
+    RtR = np.einsum("bij,bik->bjk", R, R)
+    assert np.abs(RtR - np.eye(3)).max() < 1e-12                     # K3: orthonormal frames
+    assert np.abs(np.linalg.det(R[::1000]) - 1).max() < 1e-12
+    # reach: the tip cannot be farther from the entry point than the inserted arc length
+    q = jv.cpu().numpy()
+    arc = q[:, 1] + q[:, 4]
+    Init = np.array(list(d.init_trafo))
+    assert (np.linalg.norm(T[:, 9:] - Init[9:], axis=1) <= arc + 1e-12).all()
+    # K2: theta-equivariance  T(theta) = Init Rz(theta) Init^-1 T(0)
+    jv0 = jv.clone(); jv0[:, 0] = 0.0
+    eng.batch(jv0, B, 1, nsamples=256, tip=tip2, stream=st)
+    torch.cuda.synchronize()
+    T0 = tip2.cpu().numpy()
+    Ri = Init[:9].reshape(3, 3).T; pi = Init[9:]
+    G = Ri @ rz_batch(q[:, 0]) @ Ri.T                                 # [B,3,3]
+    R0 = T0[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
+    assert np.abs(G @ R0 - R).max() < 1e-13
+    p_want = np.einsum("bij,bj->bi", G, T0[:, 9:] - pi) + pi
+    assert np.abs(p_want - T[:, 9:]).max() < 1e-13
+    # a seeded slice against the oracle
+    sl = slice(500_000, 500_000 + 50_000)
+    o = oracle.fk_batch(d, q[sl], 1, nsamples=256)
+    dp, ang = util.pose_errors(o["tip"], T[sl])
+    assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+
+
+def test_single_tube_closed_form_on_gpu(ctrfk, dev):
+    """K1 through the CUDA path: one CC tube -> circular arc, independent of N."""
+    d = ctrfk.RobotDesc()
+    d.nsections = 1; d.max_samples = 1024
+    for i, v in enumerate([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]):
+        d.init_trafo[i] = v
+    d.sec[0].ntube = 1; d.sec[0].length = 0.08; d.sec[0].stiffness[0] = 3.0
+    d.sec[0].curvature[0] = 40.0; d.sec[0].radius[0] = 1e-3; d.sec[0].poisson[0] = 0.3
+    eng = ctrfk.Engine(d, 0)
+    phi = np.linspace(0.001, 0.08, 64)
+    jv = np.stack([np.zeros_like(phi), phi, np.full_like(phi, 1.3)], axis=1)
+    for ns in (2, 16, 256, 1024):
+        g = run_gpu(ctrfk, eng, jv, 1, nsamples=ns)
+        want = np.stack([(1 - np.cos(40.0 * phi)) / 40.0, np.zeros_like(phi), np.sin(40.0 * phi) / 40.0], axis=1)
+        assert np.abs(g["tip"][:, 9:] - want).max() < 1e-14 * ns + 1e-15
+    eng.close()

@@ -1,0 +1,104 @@
+"""The kernels' per-thread solvers (csrc/ctr_fk_core.cuh), compiled for the CPU by tests/hostsim,
+against the oracle.  This checks the kernel LOGIC (control scalars, sweep order, the FAST
+reformulation) where there is no GPU; the GPU parity tests proper are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import util
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+@pytest.mark.parametrize("fast", [0, 1])
+def test_solvers_match_oracle(ctrfk, oracle, hostsim, robots, name, fast):
+    d = robots[name]
+    jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name], 0, 3000), util.edge_joint_sets(d)])
+    for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=256)), (ctrfk.MODE_STEP, dict(step=d.max_length / 256.0)),
+                     (ctrfk.MODE_NSAMPLE, dict(nsamples=1)), (ctrfk.MODE_NSAMPLE, dict(nsamples=7)),
+                     (ctrfk.MODE_STEP, dict(step=0.01)), (ctrfk.MODE_STEP, dict(step=2e-5))):
+        o = oracle.fk_batch(d, jv, mode, **kw)
+        s = util.hostsim_fk(hostsim, d, jv, mode, fast=fast, **kw)
+        assert np.array_equal(o["n"], s["n"])
+        assert np.array_equal(o["step"], s["step"])
+        dp, ang = util.pose_errors(o["tip"], s["tip"])
+        # strict: same arithmetic up to the association of the frame product.  fast: the series
+        # form of the SE(3) step is MORE accurate than the reference's closed form, which loses
+        # 1-cos(h|u|) to cancellation when h|u| < 1e-7 (section with kappa = 1e-6); the gap is
+        # largest for very coarse sampling (N = 1: 5e-11 m).  See DESIGN.md "FAST vs STRICT".
+        assert dp.max() < (2e-10 if fast else 2e-14), (mode, kw, dp.max())
+        assert ang.max() < (1e-11 if fast else 1e-13), (mode, kw, ang.max())
+        assert np.abs(o["alpha_base"] - s["alpha_base"]).max() < 1e-10
+
+
+def test_coarse_steps_take_the_closed_form_branch(ctrfk, oracle, hostsim, robots):
+    """h|u| > 0.5 rad per step: FAST leaves the series for the closed form."""
+    d = robots["ctr_sec2_tub3.xml"]
+    jv = ctrfk.sample_joints_host(d, 11, 0, 500)
+    for ns in (2, 3, 5):
+        o = oracle.fk_batch(d, jv, ctrfk.MODE_NSAMPLE, nsamples=ns)
+        s = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=ns, fast=1)
+        dp, ang = util.pose_errors(o["tip"], s["tip"])
+        assert dp.max() < 1e-12 and ang.max() < 1e-12
+
+
+def test_step_mode_dropped_tip_sample_is_reproduced(ctrfk, oracle, hostsim, robots):
+    d = ctrfk.RobotDesc.from_buffer_copy(robots["ctr_sec3_tub4.xml"])
+    d.max_samples = 64
+    jv = ctrfk.sample_joints_host(d, 1234, 0, 4000)
+    step = d.max_length / 64.0
+    o = oracle.fk_batch(d, jv, ctrfk.MODE_STEP, step=step)
+    for fast in (0, 1):
+        s = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_STEP, step=step, fast=fast)
+        assert np.array_equal(o["n"], s["n"])
+        dp, ang = util.pose_errors(o["tip"], s["tip"])
+        assert dp.max() < (2e-10 if fast else 1e-13) and ang.max() < 1e-11
+
+
+def test_phi_out_of_range_is_flagged(ctrfk, hostsim, robots):
+    d = robots["ctr_sec2_tub3.xml"]
+    jv = ctrfk.sample_joints_host(d, 1, 0, 4)
+    jv[1, 1] = 0.07      # > Length
+    jv[2, 4] = -1e-9
+    s = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=16)
+    assert list(s["n"]) == [16, 0, 0, 16]
+    assert np.isnan(s["tip"][1]).all() and np.isfinite(s["tip"][0]).all()
+
+
+def test_fast_sincos_accuracy(hostsim):
+    import mpmath as mp
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-50, 50, 20000), rng.uniform(-1e4, 1e4, 5000), np.linspace(-7, 7, 3001),
+                        np.array([0.0, np.pi / 4, np.pi / 2, np.pi, 1.5 * np.pi, 2 * np.pi, 1e-300, -1e-8])])
+    s = np.empty_like(x); c = np.empty_like(x)
+    hostsim.hostsim_sincos(x.ctypes.data, x.size, s.ctypes.data, c.ctypes.data)
+    # libm is within 1 ulp; allow 2 ulp total against it, and check a subset against mpmath
+    assert np.abs(s - np.sin(x)).max() < 3e-16 and np.abs(c - np.cos(x)).max() < 3e-16
+    mp.mp.dps = 40
+    for i in range(0, x.size, 997):
+        assert abs(mp.sin(mp.mpf(float(x[i]))) - mp.mpf(float(s[i]))) < 2.3e-16
+        assert abs(mp.cos(mp.mpf(float(x[i]))) - mp.mpf(float(c[i]))) < 2.3e-16
+    # huge / non-finite arguments go to libm
+    y = np.array([1e9, -3e7, np.inf, np.nan]); s2 = np.empty(4); c2 = np.empty(4)
+    hostsim.hostsim_sincos(y.ctypes.data, 4, s2.ctypes.data, c2.ctypes.data)
+    assert s2[0] == np.sin(1e9) and c2[1] == np.cos(-3e7) and np.isnan(s2[2]) and np.isnan(c2[3])
+
+
+def test_se3_step_series_against_mpmath(hostsim):
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        u = rng.uniform(-60, 60, 3) * rng.choice([1.0, 1e-3, 1e-7])
+        h = rng.choice([3.9e-4, 1e-3, 5e-3, 2e-2])
+        st = np.zeros(12); f = np.zeros(7)
+        hostsim.hostsim_se3(u[0], u[1], u[2], h, st.ctypes.data, f.ctypes.data)
+        ux, uy, uz = [mp.mpf(float(v)) for v in u]
+        n = mp.sqrt(ux * ux + uy * uy + uz * uz)
+        t = mp.mpf(float(h)) * n
+        B = (1 - mp.cos(t)) / n ** 2
+        Cc = (t - mp.sin(t)) / n ** 3
+        p = [B * uy + Cc * ux * uz, -B * ux + Cc * uy * uz, mp.mpf(float(h)) - Cc * (ux * ux + uy * uy)]
+        q = [mp.cos(t / 2)] + [mp.sin(t / 2) / n * v for v in (ux, uy, uz)]
+        for i in range(3):
+            assert abs(mp.mpf(float(f[4 + i])) - p[i]) < 1e-18 + 3e-16 * abs(p[i])
+        for i in range(4):
+            assert abs(mp.mpf(float(f[i])) - q[i]) < 3e-16

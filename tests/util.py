@@ -1,0 +1,85 @@
+"""Shared helpers of the test suite."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+ROBOT_FILES = ["ctr_sec2_tub3.xml", "ctr_sec3_tub3.xml", "ctr_sec3_tub4.xml", "ctr_sec3_tub5.xml"]
+SEEDS = {"ctr_sec2_tub3.xml": 20171, "ctr_sec3_tub3.xml": 20172, "ctr_sec3_tub4.xml": 20173,
+         "ctr_sec3_tub5.xml": 20174}
+
+# Parity gate of BASELINE.json north_star: tip position within 1e-9 m, orientation within 1e-9 rad.
+TOL_POS = 1e-9
+TOL_ROT = 1e-9
+
+
+def load_hostsim():
+    """CPU build of the kernels' per-thread solvers (tests/hostsim) — test harness only."""
+    d = os.path.join(HERE, "hostsim")
+    so = os.path.join(d, "libhostsim.so")
+    src = os.path.join(d, "hostsim.cpp")
+    core = os.path.join(REPO, "ram2017-ctr-kinematics_b200", "csrc", "ctr_fk_core.cuh")
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-march=x86-64-v3", "-ffp-contract=off",
+                               "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.hostsim_fk.restype = C.c_int
+    lib.hostsim_fk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hostsim_sincos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.hostsim_se3.argtypes = [C.c_double] * 4 + [C.c_void_p] * 2
+    return lib
+
+
+def hostsim_fk(lib, desc, jv, mode, step=0.0, nsamples=0, fast=1):
+    jv = np.ascontiguousarray(jv, dtype=np.float64)
+    B = jv.shape[0]
+    T = sum(desc.sec[i].ntube for i in range(desc.nsections))
+    tip = np.full((B, 12), np.nan)
+    n = np.zeros(B, np.int32)
+    st = np.zeros(B)
+    ab = np.full((B, T), np.nan)
+    rc = lib.hostsim_fk(C.addressof(desc), jv.ctypes.data, B, mode, step, nsamples, fast, tip.ctypes.data,
+                        n.ctypes.data, st.ctypes.data, ab.ctypes.data, None)
+    assert rc == 0
+    return dict(tip=tip, n=n, step=st, alpha_base=ab)
+
+
+def pose_errors(tip_a, tip_b):
+    """Per-configuration (position error [m], geodesic rotation angle [rad]) between two [B,12]
+    column-major 3x4 batches."""
+    a = np.asarray(tip_a).reshape(-1, 12)
+    b = np.asarray(tip_b).reshape(-1, 12)
+    dp = np.linalg.norm(a[:, 9:] - b[:, 9:], axis=1)
+    fro = np.linalg.norm(a[:, :9] - b[:, :9], axis=1)           # |Ra - Rb|_F = 2 sqrt2 sin(angle/2)
+    ang = 2.0 * np.arcsin(np.clip(fro / (2.0 * np.sqrt(2.0)), 0.0, 1.0))
+    return dp, ang
+
+
+def edge_joint_sets(desc):
+    """Edge cases of SURVEY.md §8d: phi = 0, phi = L, all phi = 0, alpha in {0, pi, 2pi^-}."""
+    S = desc.nsections
+    nj = 1 + S + sum(desc.sec[i].ntube for i in range(S))
+    two_pi_m = np.nextafter(2 * np.pi, 0.0)
+    phi_idx, alpha_idx, t0 = [], [], 0
+    for s in range(S):
+        phi_idx.append(1 + s + t0)
+        for k in range(desc.sec[s].ntube):
+            alpha_idx.append(2 + s + t0 + k)
+        t0 += desc.sec[s].ntube
+    lens = [desc.sec[s].length for s in range(S)]
+    rows = []
+    rng = np.random.default_rng(7)
+    for phis in ([0.0] * S, lens, [0.5 * l for l in lens]) + tuple([[lens[i] if i == j else 0.0 for i in range(S)] for j in range(S)]):
+        for a in (0.0, np.pi, two_pi_m, None):
+            q = np.zeros(nj)
+            q[0] = 0.7
+            for i, p in zip(phi_idx, phis):
+                q[i] = p
+            for i in alpha_idx:
+                q[i] = a if a is not None else rng.uniform(0, two_pi_m)
+            rows.append(q)
+    return np.array(rows)
