@@ -297,6 +297,17 @@ def main():
     h_jv = torch.empty(B, njv, dtype=torch.float64).pin_memory()
     h_tip = torch.empty(B, 12, dtype=torch.float64).pin_memory()
     h_jv.copy_(jvs[0].cpu())
+    # PCIe copy rates with the same pinned buffers: the bound of the end-to-end number
+    pcie = {}
+    for name, dst, src in (("h2d_GBs", jvs[1], h_jv), ("d2h_GBs", h_tip, tips[1])):
+        best = 0.0
+        for _ in range(3):
+            ev0.record()
+            dst.copy_(src, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            best = max(best, src.numel() * 8 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
+        pcie[name] = best
     e2e = None
     if not a.backbone and not a.f32:
         e2e_steps = max(3, min(a.steps, 10))
@@ -313,7 +324,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * e2e_steps / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": B * njv * 8, "d2h_bytes_per_step": B * 12 * 8, "steps": e2e_steps,
-               "api": "ctr_fk_batch_host (host pointers in, tip poses out; chunked H2D/solve/D2H on 3 streams)"}
+               "api": "ctr_fk_batch_host (host pointers in, tip poses out; chunked H2D/solve/D2H on 3 streams)",
+               "pcie_measured": pcie,
+               "bound": "PCIe: %.0f MB out per step at the measured D2H rate caps this at %.3g configurations/s" % (
+                   B * 96 / 1e6, B / (B * 96 / 1e9 / pcie["d2h_GBs"]))}
         assert bool(torch.isfinite(h_tip).all())
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ---------------------------

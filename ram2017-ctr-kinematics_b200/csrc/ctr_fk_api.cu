@@ -28,14 +28,18 @@ struct ctr_fk_engine {
     cudaStream_t   streams[kStreams];
     std::mutex     host_mu;      // serialises ctr_fk_batch_host / ctr_fk_single calls on one handle
     char*          single_buf;   // device scratch of ctr_fk_single (lazily allocated)
+    char*          stage_buf;    // device staging slabs of ctr_fk_batch_host (grow-only, cached)
+    size_t         stage_bytes;
 };
 
 namespace {
 
 // configurations below this count are not worth three extra launches for binning
 constexpr int64_t kMinBinBatch = 8192;
+// the binning kernels keep 2 x (MaxSamples + 2) counters in shared memory
+constexpr int kMaxBinSamples = 4096;
 // host-pointer path: configurations per pipelined chunk
-constexpr int64_t kHostChunk = 131072;
+constexpr int64_t kHostChunk = 65536;   // 6.3 MB out per chunk: PCIe-bound, short pipeline fill/drain
 
 struct DeviceGuard {
     int prev = -1;
@@ -89,7 +93,7 @@ cudaError_t make_order(ctr_fk_handle h, const double* jv, int64_t B, int mode, d
     e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)nbins, st);
     if (e == cudaSuccess) e = launch_count_samples(h->key, h->rb, jv, B, mode, step, ns, n, hist, st);
     if (e == cudaSuccess) e = launch_bin_offsets(hist, nbins, st);
-    if (e == cudaSuccess) e = launch_bin_scatter(n, B, hist, order, st);
+    if (e == cudaSuccess) e = launch_bin_scatter(n, B, hist, order, nbins, st);
     cudaFreeAsync(n, st);
     cudaFreeAsync(hist, st);
     if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
@@ -109,7 +113,7 @@ int run_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double ste
     a.backbone = backbone; a.radius = radius; a.soa = (flags & CTR_FK_FLAG_SOA) ? 1 : 0;
 
     int32_t* order = nullptr;
-    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch) {
+    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples) {
         cudaError_t e = make_order(h, jv, B, mode, step, nsamples, &order, st);
         if (e != cudaSuccess) return cuda_fail("step-mode binning", e);
         a.order = order;
@@ -157,6 +161,8 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
     h->sm_count = prop.multiProcessorCount;
     for (int i = 0; i < ctr_fk_engine::kStreams; ++i) h->streams[i] = nullptr;
     h->single_buf = nullptr;
+    h->stage_buf = nullptr;
+    h->stage_bytes = 0;
     for (int i = 0; i < ctr_fk_engine::kStreams; ++i) {
         if ((e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
             for (int j = 0; j < i; ++j) cudaStreamDestroy(h->streams[j]);
@@ -176,6 +182,7 @@ int ctr_fk_destroy(ctr_fk_handle h)
         for (int i = 0; i < ctr_fk_engine::kStreams; ++i)
             if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
         if (h->single_buf) cudaFree(h->single_buf);
+        if (h->stage_buf) cudaFree(h->stage_buf);
     }
     delete h;
     return 0;
@@ -220,9 +227,18 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     const size_t off_stat = off_step + sizeof(double) * (size_t)chunk;
     const size_t slab     = ((off_stat + sizeof(int32_t) * (size_t)chunk * 2 + 255) / 256) * 256;
     const int nslab = (int)std::min<int64_t>(NS, (B + chunk - 1) / chunk);
-    char* dbuf = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dbuf, slab * (size_t)nslab);
-    if (e != cudaSuccess) return cuda_fail("ctr_fk_batch_host: device staging allocation", e);
+    // staging slabs are cached in the handle: cudaMalloc/cudaFree per call would add milliseconds
+    // and a device-wide synchronisation to every batch
+    cudaError_t e = cudaSuccess;
+    if (h->stage_bytes < slab * (size_t)nslab) {
+        if (h->stage_buf) cudaFree(h->stage_buf);
+        h->stage_buf = nullptr;
+        h->stage_bytes = 0;
+        e = cudaMalloc((void**)&h->stage_buf, slab * (size_t)nslab);
+        if (e != cudaSuccess) return cuda_fail("ctr_fk_batch_host: device staging allocation", e);
+        h->stage_bytes = slab * (size_t)nslab;
+    }
+    char* dbuf = h->stage_buf;
 
     int ret = 0;
     int64_t done = 0;
@@ -248,7 +264,6 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
         e = cudaStreamSynchronize(h->streams[i]);
         if (e != cudaSuccess && ret == 0) ret = cuda_fail("ctr_fk_batch_host: stream sync", e);
     }
-    cudaFree(dbuf);
     return ret;
 }
 
@@ -305,7 +320,7 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
     a.tip = tip; a.n_out = n_out; a.step_out = step_out; a.status = status;
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* order = nullptr;
-    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch) {
+    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples) {
         cudaError_t e = make_order(h, jv, B, mode, step, nsamples, &order, st);
         if (e != cudaSuccess) return cuda_fail("step-mode binning", e);
         a.order = order;

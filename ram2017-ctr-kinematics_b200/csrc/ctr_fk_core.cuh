@@ -350,257 +350,547 @@ CTR_HD void solve_strict(const KRobot& rb, const Ctl<L>& c, double* tip, double*
 }
 
 // ---- FAST building blocks ---------------------------------------------------------------------
+//
+// Throughput notes (B200, measured: profiles/): an FP64 instruction keeps the SM sub-partition's
+// FP64 pipe busy for 2 cycles while the scheduler can issue 1 instruction per cycle, so the sweep
+// is FP64-pipe bound only while it issues fewer non-FP64 than FP64 instructions.  Hence:
+//   * every polynomial coefficient lives in __constant__ memory and is consumed as a c[bank][off]
+//     operand of the DFMA itself (a literal double costs two extra MOVs per use);
+//   * sign flips, quadrant swaps, interval masks and range guards are integer/select operations on
+//     the bit patterns, which run on the otherwise idle ALU pipe;
+//   * rarely taken branches (huge angles, coarse steps, zero curvature) are kept out of line.
 
-// sin and cos of a moderate argument (|x| < ~1e5): k = rint(x*2/pi), r = x - k*pi/2 by a 3-term
-// Cody-Waite split (exact products for |k| < 2^20 or so), minimax-grade Taylor kernels on
-// |r| <= pi/4 (degree 13 / 14), quadrant fix-up in integer arithmetic.  Max error ~1 ulp.
-// Falls back to libm for huge or non-finite arguments.
+struct FastConsts {
+    double two_over_pi, magic, p1, p2, p3;
+    double s[6];      // sin kernel, Horner order (highest degree first)
+    double c[6];      // cos kernel
+    double qa4[4], qb4[4], qc4[4];   // SE(3) series for m <= 2^-8, Horner order
+    double qa8[7], qb8[7], qc8[7];   // SE(3) series for m <= 2^-4
+};
+
+#define CTRK_FAST_CONSTS_INIT                                                                      \
+    {                                                                                              \
+        6.36619772367581382433e-01, 6755399441055744.0, 1.57079632673412561417e+00,                \
+            6.07710050650619224932e-11, 2.02226624879595063154e-21,                                \
+            {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,  \
+             -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01},\
+            {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, \
+             2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02}, \
+            {1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5},                                       \
+            {1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0},                              \
+            {256.0 / 39916800.0, -64.0 / 362880.0, 16.0 / 5040.0, -4.0 / 120.0},                   \
+            {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0,             \
+             -1.0 / 720.0, 1.0 / 24.0, -0.5},                                                      \
+            {-1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0,        \
+             -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0},                                              \
+            {4096.0 / 1307674368000.0, -1024.0 / 6227020800.0, 256.0 / 39916800.0,                 \
+             -64.0 / 362880.0, 16.0 / 5040.0, -4.0 / 120.0, 1.0 / 6.0}                             \
+    }
+// NB: qc8's last entry is the constant term 1/6 (its Horner chain has no separate "+1" step).
+
+#if defined(__CUDACC__)
+static __constant__ FastConsts kFastDev = CTRK_FAST_CONSTS_INIT;
+#endif
+static const FastConsts kFastHost = CTRK_FAST_CONSTS_INIT;
+
+#ifdef __CUDA_ARCH__
+#define CTRK_FC kFastDev
+#else
+#define CTRK_FC kFastHost
+#endif
+
+// bit-pattern helpers (integer pipe)
+CTR_HD int hi_word(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    union { double d; uint64_t u; } v; v.d = x;
+    return (int)(uint32_t)(v.u >> 32);
+#endif
+}
+CTR_HD int lo_word(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    union { double d; uint64_t u; } v; v.d = x;
+    return (int)(uint32_t)v.u;
+#endif
+}
+CTR_HD double xor_sign(double x, int mask_hi)      // flips the sign iff mask_hi == 0x80000000
+{
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) ^ mask_hi, __double2loint(x));
+#else
+    union { double d; uint64_t u; } v; v.d = x;
+    v.u ^= ((uint64_t)(uint32_t)mask_hi) << 32;
+    return v.d;
+#endif
+}
+// a <= b for doubles known to be >= +0 (or a negative a): signed compare of the bit patterns
+CTR_HD bool le_nonneg(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(a) <= __double_as_longlong(b);
+#else
+    union { double d; int64_t i; } x, y; x.d = a; y.d = b;
+    return x.i <= y.i;
+#endif
+}
+CTR_HD double libm_sincos_s(double x, double* c)
+{
+    double s;
+#ifdef __CUDA_ARCH__
+    sincos(x, &s, c);
+#else
+    s = sin(x); *c = cos(x);
+#endif
+    return s;
+}
+
+// sin and cos for |x| < 1024 (the caller guards the range): k = rint(x*2/pi) by the magic-number
+// trick, r = x - k*pi/2 with a 2-term Cody-Waite split (k*p1 exact for |k| < 2^20; the dropped
+// third term is < 1.4e-18 for |k| <= 652), fdlibm kernel polynomials on |r| <= pi/4, quadrant
+// fix-up on the bit patterns.  Error < 1 ulp.  22 FP64 instructions.
+CTR_HD void sincos_bounded(double x, double& s_out, double& c_out)
+{
+    const double kd_m = x_fma(x, CTRK_FC.two_over_pi, CTRK_FC.magic);
+    const double kd   = kd_m - CTRK_FC.magic;
+    const int    q    = lo_word(kd_m);
+    double r = x_fma(-kd, CTRK_FC.p1, x);
+    r        = x_fma(-kd, CTRK_FC.p2, r);
+    const double z = r * r;
+    double ps = x_fma(CTRK_FC.s[0], z, CTRK_FC.s[1]);
+    double pc = x_fma(CTRK_FC.c[0], z, CTRK_FC.c[1]);
+    ps = x_fma(ps, z, CTRK_FC.s[2]);
+    pc = x_fma(pc, z, CTRK_FC.c[2]);
+    ps = x_fma(ps, z, CTRK_FC.s[3]);
+    pc = x_fma(pc, z, CTRK_FC.c[3]);
+    ps = x_fma(ps, z, CTRK_FC.s[4]);
+    pc = x_fma(pc, z, CTRK_FC.c[4]);
+    ps = x_fma(ps, z, CTRK_FC.s[5]);
+    pc = x_fma(pc, z, CTRK_FC.c[5]);
+    const double sr = x_fma(r * z, ps, r);
+    const double cr = x_fma(z * z, pc, x_fma(-0.5, z, 1.0));
+    const bool   sw = (q & 1) != 0;
+    const double s1 = sw ? cr : sr;
+    const double c1 = sw ? sr : cr;
+    s_out = xor_sign(s1, (q & 2) << 30);
+    c_out = xor_sign(c1, ((q + 1) & 2) << 30);
+}
+
+// General-purpose version (any finite or non-finite x): used once per configuration for the
+// final Rz and in the backbone pass.
 CTR_HD void fast_sincos(double x, double& s_out, double& c_out)
 {
-    if (!(fabs(x) < 1.0e5)) {
-#ifdef __CUDA_ARCH__
-        sincos(x, &s_out, &c_out);
-#else
-        s_out = sin(x); c_out = cos(x);
-#endif
+    if ((hi_word(x) & 0x7fffffff) < 0x40900000) {      // |x| < 1024
+        sincos_bounded(x, s_out, c_out);
         return;
     }
-    const double two_over_pi = 6.36619772367581382433e-01;
-    const double magic = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest-integer trick
-    const double kd_m  = x_fma(x, two_over_pi, magic);
-    const double kd    = kd_m - magic;
-#ifdef __CUDA_ARCH__
-    const int q = __double2loint(kd_m);
-#else
-    union { double d; uint64_t u; } cvt; cvt.d = kd_m;
-    const int q = (int)(uint32_t)cvt.u;
-#endif
-    // pi/2 = p1 + p2 + p3, p1 and p2 with 33 significant bits
-    const double p1 = 1.57079632673412561417e+00;
-    const double p2 = 6.07710050630396597660e-11;
-    const double p3 = 2.02226624879595063154e-21;
-    double r = x_fma(-kd, p1, x);
-    r = x_fma(-kd, p2, r);
-    r = x_fma(-kd, p3, r);
-    const double z = r * r;
-    // sin(r) = r + r*z*(S1 + z*(S2 + ... S6))      (fdlibm __kernel_sin coefficients)
-    double ps = 1.58969099521155010221e-10;
-    ps = x_fma(ps, z, -2.50507602534068634195e-08);
-    ps = x_fma(ps, z, 2.75573137070700676789e-06);
-    ps = x_fma(ps, z, -1.98412698298579493134e-04);
-    ps = x_fma(ps, z, 8.33333333332248946124e-03);
-    ps = x_fma(ps, z, -1.66666666666666324348e-01);
-    const double sr = x_fma(r * z, ps, r);
-    // cos(r) = 1 - z/2 + z*z*(C1 + z*(C2 + ... C6))  (fdlibm __kernel_cos coefficients)
-    double pc = -1.13596475577881948265e-11;
-    pc = x_fma(pc, z, 2.08757232129817482790e-09);
-    pc = x_fma(pc, z, -2.75573143513906633035e-07);
-    pc = x_fma(pc, z, 2.48015872894767294178e-05);
-    pc = x_fma(pc, z, -1.38888888888741095749e-03);
-    pc = x_fma(pc, z, 4.16666666666666019037e-02);
-    const double cr = x_fma(z * z, pc, x_fma(-0.5, z, 1.0));
-    // quadrant: q&1 swaps, bit 1 of q negates sin, bit 1 of (q+1) negates cos
-    const double s1 = (q & 1) ? cr : sr;
-    const double c1 = (q & 1) ? sr : cr;
-    s_out = (q & 2) ? -s1 : s1;
-    c_out = ((q + 1) & 2) ? -c1 : c1;
+    s_out = libm_sincos_s(x, &c_out);
 }
 
-// Series used by the FAST SE(3) step, in m = (h|u|/2)^2 (half-angle squared):
-//   qa(m) = cos(sqrt m)            = 1 - m/2 + m^2/24 - ...
-//   qb(m) = sin(sqrt m)/sqrt m     = 1 - m/6 + m^2/120 - ...
+// Series of the SE(3) step in m = (h|u|/2)^2 (half-angle squared):
+//   qa(m) = cos(sqrt m)                    = 1 - m/2 + m^2/24 - ...
+//   qb(m) = sin(sqrt m)/sqrt m             = 1 - m/6 + m^2/120 - ...
 //   qc(m) = (t - sin t)/t^3, t = 2 sqrt m  = 1/6 - 4m/120 + 16 m^2/5040 - ...
-// Truncated after m^7; for m <= kFastM the truncation error is below 1e-18.
-constexpr double kFastM = 0.0625;   // |h u| <= 0.5 rad per step
+// Tier 1 (m <= 2^-8, i.e. h|u| <= 0.125 rad per step: every step of the benchmark workloads):
+// through m^4, truncation < 3e-19.  Tier 2 (m <= 2^-4): through m^7, truncation < 1e-18.
+constexpr double kFastM1 = 0.00390625;   // 2^-8
+constexpr double kFastM2 = 0.0625;       // 2^-4
+constexpr double kFastM  = kFastM2;
 
-CTR_HD void se3_series(double m, double& qa, double& qb, double& qc)
+CTR_HD void se3_series4(double m, double& qa, double& qb, double& qc)
 {
-    double a = -1.0 / 87178291200.0;                 // -1/14!
-    a = x_fma(a, m, 1.0 / 479001600.0);              //  1/12!
-    a = x_fma(a, m, -1.0 / 3628800.0);               // -1/10!
-    a = x_fma(a, m, 1.0 / 40320.0);
-    a = x_fma(a, m, -1.0 / 720.0);
-    a = x_fma(a, m, 1.0 / 24.0);
-    a = x_fma(a, m, -0.5);
+    double a = x_fma(CTRK_FC.qa4[0], m, CTRK_FC.qa4[1]);
+    double b = x_fma(CTRK_FC.qb4[0], m, CTRK_FC.qb4[1]);
+    double c = x_fma(CTRK_FC.qc4[0], m, CTRK_FC.qc4[1]);
+    a = x_fma(a, m, CTRK_FC.qa4[2]);
+    b = x_fma(b, m, CTRK_FC.qb4[2]);
+    c = x_fma(c, m, CTRK_FC.qc4[2]);
+    a = x_fma(a, m, CTRK_FC.qa4[3]);
+    b = x_fma(b, m, CTRK_FC.qb4[3]);
+    c = x_fma(c, m, CTRK_FC.qc4[3]);
     qa = x_fma(a, m, 1.0);
-    double b = -1.0 / 1307674368000.0;               // -1/15!
-    b = x_fma(b, m, 1.0 / 6227020800.0);             //  1/13!
-    b = x_fma(b, m, -1.0 / 39916800.0);              // -1/11!
-    b = x_fma(b, m, 1.0 / 362880.0);
-    b = x_fma(b, m, -1.0 / 5040.0);
-    b = x_fma(b, m, 1.0 / 120.0);
-    b = x_fma(b, m, -1.0 / 6.0);
     qb = x_fma(b, m, 1.0);
-    // (t - sin t)/t^3 = sum_{j>=0} (-1)^j t^(2j)/(2j+3)!,  t^2 = 4m
-    double cc = 4096.0 / 1307674368000.0;            // +4^6/15!
-    cc = x_fma(cc, m, -1024.0 / 6227020800.0);       // -4^5/13!
-    cc = x_fma(cc, m, 256.0 / 39916800.0);           // +4^4/11!
-    cc = x_fma(cc, m, -64.0 / 362880.0);             // -4^3/9!
-    cc = x_fma(cc, m, 16.0 / 5040.0);                // +4^2/7!
-    cc = x_fma(cc, m, -4.0 / 120.0);                 // -4/5!
-    qc = x_fma(cc, m, 1.0 / 6.0);
+    qc = x_fma(c, m, 1.0 / 6.0);
 }
 
-// One SE(3) step as (unit quaternion (qw, qv), translation pe), FAST form.
+CTR_HD void se3_series8(double m, double& qa, double& qb, double& qc)
+{
+    double a = CTRK_FC.qa8[0], b = CTRK_FC.qb8[0], c = CTRK_FC.qc8[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) {
+        a = x_fma(a, m, CTRK_FC.qa8[i]);
+        b = x_fma(b, m, CTRK_FC.qb8[i]);
+        c = x_fma(c, m, CTRK_FC.qc8[i]);
+    }
+    qa = x_fma(a, m, 1.0);
+    qb = x_fma(b, m, 1.0);
+    qc = c;
+}
+
+// One SE(3) step as (unit quaternion, translation), FAST form.
 //   rotation  exp(h [u]x)  ->  qw = cos(t/2), qv = sin(t/2)/|u| * u,  t = h|u|
 //   translation (robot_i.h:1257-1259, exact arc integral):
 //       pe = h e3 + B (u x e3) + C (u u_z - |u|^2 e3),  B = (1-cos t)/|u|^2, C = (t-sin t)/|u|^3
-CTR_HD void se3_step_fast(double ux, double uy, double uz, double h, double ztol, double& qw,
-                          double& qx, double& qy, double& qz, double& px, double& py, double& pz)
+struct StepConsts {      // per-configuration constants of the step
+    double h, hh, hh2, h3, ztol2;
+};
+CTR_HD StepConsts make_step_consts(double h, double ztol)
+{
+    StepConsts k;
+    k.h = h; k.hh = 0.5 * h; k.hh2 = k.hh * k.hh; k.h3 = h * h * h; k.ztol2 = ztol * ztol;
+    return k;
+}
+
+// Cold part: zero curvature (reference quirk), tier 2, closed form.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+inline void se3_step_cold(double ux, double uy, double uz, double sxy, double n2, double m,
+                          double h, double hh, double h3, double ztol2,
+                          double* o /* qw qx qy qz px py pz */)
+{
+    // scalars by value on purpose: taking the address of the caller's state would force the
+    // whole sweep state into local memory
+    if (n2 < ztol2) {
+        // |u| "equals" zero: the reference returns the identity rotation and a translation of
+        // h*|u| (~0, not h) along z (robot_i.h:1245, :1264-1266; SURVEY §8g-7).  Reproduced.
+        o[0] = 1.0; o[1] = o[2] = o[3] = 0.0; o[4] = o[5] = 0.0; o[6] = h * sqrt(n2);
+        return;
+    }
+    if (m <= kFastM2) {
+        double qa, qb, qc;
+        se3_series8(m, qa, qb, qc);
+        const double b  = hh * qb;
+        const double b2 = 2.0 * b;
+        const double C  = h3 * qc;
+        const double cz = C * uz;
+        o[0] = qa; o[1] = b * ux; o[2] = b * uy; o[3] = b * uz;
+        o[4] = x_fma(cz, ux, b2 * o[2]);
+        o[5] = x_fma(cz, uy, -(b2 * o[1]));
+        o[6] = x_fma(-C, sxy, h);
+        return;
+    }
+    const double nrm = sqrt(n2);
+    const double t = h * nrm;
+    double ch, ct;
+    const double sh = libm_sincos_s(0.5 * t, &ch);
+    const double st = libm_sincos_s(t, &ct);
+    const double b = sh / nrm;
+    o[0] = ch; o[1] = b * ux; o[2] = b * uy; o[3] = b * uz;
+    const double Bc = (1.0 - ct) / n2;
+    const double C  = (t - st) / (n2 * nrm);
+    o[4] = Bc * uy + C * ux * uz;
+    o[5] = -Bc * ux + C * uy * uz;
+    o[6] = h - C * sxy;
+}
+
+CTR_HD void se3_step_fast_k(double ux, double uy, double uz, const StepConsts& k, double& qw,
+                            double& qx, double& qy, double& qz, double& px, double& py, double& pz)
 {
     const double sxy = x_fma(uy, uy, ux * ux);
     const double n2  = x_fma(uz, uz, sxy);
-    const double hh  = 0.5 * h;
-    const double m   = n2 * (hh * hh);
-    if (n2 < ztol * ztol) {
-        // |u| "equals" zero: the reference returns the identity rotation and a translation of
-        // h*|u| (~0, not h) along z (robot_i.h:1245, :1264-1266; SURVEY §8g-7).  Reproduced.
-        qw = 1.0; qx = qy = qz = 0.0; px = py = 0.0; pz = h * sqrt(n2);
-        return;
-    }
-    if (m <= kFastM) {
+    const double m   = n2 * k.hh2;
+    // hot path: ztol^2 <= n2 and m <= 2^-8, both tested on the bit patterns (values are >= 0)
+    if (le_nonneg(k.ztol2, n2) && hi_word(m) < 0x3f700000) {
         double qa, qb, qc;
-        se3_series(m, qa, qb, qc);
-        const double b  = hh * qb;               // sin(t/2)/|u|
+        se3_series4(m, qa, qb, qc);
+        const double b2 = k.h * qb;              // 2 sin(t/2)/|u|
+        const double b  = k.hh * qb;             //   sin(t/2)/|u|
         qw = qa;
         qx = b * ux; qy = b * uy; qz = b * uz;
-        const double b2 = 2.0 * b;               // B = 2 b^2
-        const double C  = (h * h * h) * qc;
+        const double C  = k.h3 * qc;
         const double cz = C * uz;
-        px = x_fma(cz, ux, b2 * qy);             // B uy + C ux uz
+        px = x_fma(cz, ux, b2 * qy);             // B uy + C ux uz,  B = 2 b^2
         py = x_fma(cz, uy, -(b2 * qx));          // -B ux + C uy uz
-        pz = x_fma(-C, sxy, h);                  // h - C (ux^2+uy^2)
+        pz = x_fma(-C, sxy, k.h);                // h - C (ux^2+uy^2)
         return;
     }
-    // large rotation per step (coarse sampling): closed form
-    const double nrm = sqrt(n2);
-    double sh, ch, st, ct;
-    const double t = h * nrm;
-#ifdef __CUDA_ARCH__
-    sincos(0.5 * t, &sh, &ch);
-    sincos(t, &st, &ct);
-#else
-    sh = sin(0.5 * t); ch = cos(0.5 * t); st = sin(t); ct = cos(t);
-#endif
-    const double b = sh / nrm;
-    qw = ch; qx = b * ux; qy = b * uy; qz = b * uz;
-    const double Bc = (1.0 - ct) / n2;
-    const double C  = (t - st) / (n2 * nrm);
-    px = Bc * uy + C * ux * uz;
-    py = -Bc * ux + C * uy * uz;
-    pz = h - C * sxy;
+    double o[7];
+    se3_step_cold(ux, uy, uz, sxy, n2, m, k.h, k.hh, k.h3, k.ztol2, o);
+    qw = o[0]; qx = o[1]; qy = o[2]; qz = o[3]; px = o[4]; py = o[5]; pz = o[6];
+}
+
+CTR_HD void se3_step_fast(double ux, double uy, double uz, double h, double ztol, double& qw,
+                          double& qx, double& qy, double& qz, double& px, double& py, double& pz)
+{
+    const StepConsts k = make_step_consts(h, ztol);
+    se3_step_fast_k(ux, uy, uz, k, qw, qx, qy, qz, px, py, pz);
 }
 
 // ---- FAST solver ---------------------------------------------------------------------------
-// Same recurrence as solve_strict; see the header comment for what differs.  After the first
-// (tip) sample tube 0's angle is pinned to 0 (section_i.h:308), so its sin/cos are (0,1) and are
-// not evaluated: the tip sample is peeled off the loop and handled by the general code.
-template <class L, class OnSample>
-CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* albase,
-                       OnSample on_sample)
-{
-    constexpr int S = L::S, T = L::T;
-    double al[T], uzs[T], sn[T], cs[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) { al[t] = c.al[t]; uzs[t] = 0.0; }
-    // accumulated suffix product  P = E_k ... E_tip  as quaternion + translation
-    double Qw = 1.0, Qx = 0.0, Qy = 0.0, Qz = 0.0, Px = 0.0, Py = 0.0, Pz = 0.0;
-    double a_tip = 0.0;
-    const double h = c.h;
-    double pos = c.arc_end;
-    const int tipk = c.nframes - 1;
+// Same recurrence as solve_strict; see the header comment for what differs.
+//
+// Structure of the sweep (k runs from N-1 at the tip down to 0 at the base):
+//   head  k = N-1   tube 0 still carries its joint angle, torsion is zero, and in step mode the
+//                   frame of this sample may be the dropped tip sample
+//   body  k = N-2..1  the hot loop
+//   tail  k = 0     no angle/torsion update
+// Two things make the body cheap:
+//   * Software pipelining: the SE(3) accumulation of sample k+1 is issued in iteration k, next to
+//     the (independent) curvature/torsion arithmetic of sample k, so the FP64 pipe always has a
+//     second dependency chain to draw from (16 warps per SM are not enough to hide DFMA latency
+//     on their own).  Iteration k leaves its sample in `pend` for iteration k-1.
+//   * Incremental trigonometry: tube angles move by d_t = h (z_t - z_0) per step, |d_t| ~ 1e-2,
+//     so sin/cos(alpha_t) are carried and rotated by (cos d_t, sin d_t) from a 4-term series
+//     instead of being re-evaluated (15 instead of 22 FP64 instructions per tube and step).  The
+//     rotation is accurate to 1 ulp per step; over N steps that adds O(N) ulp to quantities whose
+//     own rounding history (alpha_t += d_t) is of the same size.
+// A body iteration is HOT when every tube has |d_t| < 2^-4, and the pending sample has
+// ztol <= |u| and (h|u|/2)^2 < 2^-8; all benchmark workloads are 100 % hot.  Anything else (coarse
+// sampling, zero curvature) takes the generic iteration.
+#ifdef CTRK_COUNT_COLD
+static long long g_iter_total = 0, g_iter_cold = 0, g_iter_cold_delta = 0;
+#endif
+template <class L, bool WANT_TIP, class OnSample>
+struct FastSweep {
+    static constexpr int  S = L::S, T = L::T;
+    static constexpr bool want_tip = WANT_TIP;   // compile-time: keeps the accumulation of the
+                                                 // pending sample in the same basic block as the
+                                                 // arithmetic of the current one
+    const KRobot& rb;
+    const Ctl<L>& c;
+    OnSample      on_sample;
+    StepConsts    kc;
+    double al[T], uzs[T];
+    double sn[T], cs[T];               // sin/cos(al[t]) for t >= 1 (tube 0: see step())
+    double hko[T > 1 ? T - 1 : 1];     // h * (1+nu_t) * kappa_sec(t)
+    double Qw, Qx, Qy, Qz, Px, Py, Pz; // suffix product E_k ... E_tip
+    double pux, puy, puz;              // pending sample (not yet accumulated)
+    double a_tip, pos;
 
-    // per-configuration constants of the torsion step: h * onu[t] * kappa[sec(t)]
-    double hko[T > 1 ? T - 1 : 1];
+    CTR_HD FastSweep(const KRobot& rb_, const Ctl<L>& c_, const OnSample& os)
+        : rb(rb_), c(c_), on_sample(os)
+    {
+        kc = make_step_consts(c.h, rb.ztol);
 #pragma unroll
-    for (int t = 0; t + 1 < T; ++t) hko[t] = h * rb.onu[t] * rb.kappa[L::sec_of(t)];
-
-#pragma unroll 1
-    for (int k = c.n - 1; k >= 0; --k) {
-        // sin/cos of the tube angles; tube 0 is exactly 0 after the first update
-        if (k == c.n - 1) {
-            fast_sincos(al[0], sn[0], cs[0]);
-        } else {
-            sn[0] = 0.0; cs[0] = 1.0;
-        }
+        for (int t = 0; t < T; ++t) { al[t] = c.al[t]; uzs[t] = 0.0; sn[t] = 0.0; cs[t] = 1.0; }
 #pragma unroll
         for (int t = 1; t < T; ++t) fast_sincos(al[t], sn[t], cs[t]);
+#pragma unroll
+        for (int t = 0; t + 1 < T; ++t) hko[t] = c.h * rb.onu[t] * rb.kappa[L::sec_of(t)];
+        Qw = 1.0; Qx = Qy = Qz = 0.0; Px = Py = Pz = 0.0;
+        pux = puy = puz = 0.0;
+        a_tip = 0.0;
+        pos = c.arc_end;
+    }
 
-        // section masks on the exact arc position
+    // P <- E P for one step given as unit quaternion e and translation pe
+    CTR_HD void apply(double ew, double ex, double ey, double ez, double pex, double pey, double pez)
+    {
+        // translation: p <- pe + R(e) p,  R(e) v = v + 2 (w t + q x t),  t = q x v
+        const double tx = x_fma(ey, Pz, -(ez * Py));
+        const double ty = x_fma(ez, Px, -(ex * Pz));
+        const double tz = x_fma(ex, Py, -(ey * Px));
+        const double ix = x_fma(ew, tx, x_fma(ey, tz, -(ez * ty)));
+        const double iy = x_fma(ew, ty, x_fma(ez, tx, -(ex * tz)));
+        const double iz = x_fma(ew, tz, x_fma(ex, ty, -(ey * tx)));
+        Px = x_fma(2.0, ix, Px + pex);
+        Py = x_fma(2.0, iy, Py + pey);
+        Pz = x_fma(2.0, iz, Pz + pez);
+        // rotation: Q <- e (x) Q
+        const double w2 = x_fma(-ez, Qz, x_fma(-ey, Qy, x_fma(-ex, Qx, ew * Qw)));
+        const double x2 = x_fma(-ez, Qy, x_fma(ey, Qz, x_fma(ex, Qw, ew * Qx)));
+        const double y2 = x_fma(-ex, Qz, x_fma(ez, Qx, x_fma(ey, Qw, ew * Qy)));
+        const double z2 = x_fma(-ey, Qx, x_fma(ex, Qy, x_fma(ez, Qw, ew * Qz)));
+        Qw = w2; Qx = x2; Qy = y2; Qz = z2;
+    }
+    CTR_HD void accumulate_generic(double ux, double uy, double uz)
+    {
+        double ew, ex, ey, ez, px_, py_, pz_;
+        se3_step_fast_k(ux, uy, uz, kc, ew, ex, ey, ez, px_, py_, pz_);
+        apply(ew, ex, ey, ez, px_, py_, pz_);
+    }
+    // hot form: tier-1 series, no branches; sxy and m precomputed by the caller
+    CTR_HD void accumulate_hot(double ux, double uy, double uz, double sxy, double m)
+    {
+        double qa, qb, qc;
+        se3_series4(m, qa, qb, qc);
+        const double b2 = kc.h * qb;
+        const double b  = kc.hh * qb;
+        const double ex = b * ux, ey = b * uy, ez = b * uz;
+        const double C  = kc.h3 * qc;
+        const double cz = C * uz;
+        apply(qa, ex, ey, ez, x_fma(cz, ux, b2 * ey), x_fma(cz, uy, -(b2 * ex)), x_fma(-C, sxy, kc.h));
+    }
+
+    // One sample.  HEAD/TAIL as described above.  HOT: pipelined hot form; `dl[t]` = h (z_t - z_0)
+    // (angle increments, valid when !TAIL), (sxy, m) describe the pending sample (valid when HOT).
+    // ROT (with HOT): rotate the carried sin/cos by d_t; otherwise re-evaluate them from the new
+    // angles with sincos_bounded (the caller has checked |alpha_t| < 1024).
+    template <bool HEAD, bool TAIL, bool HOT, bool ROT = false>
+    CTR_HD void step(int k, const double* dl, double sxy_p, double m_p)
+    {
+        // ---- (A) accumulate the pending sample k+1 (independent of everything below) -----------
+        if (!HEAD && want_tip) {
+            if (HOT) accumulate_hot(pux, puy, puz, sxy_p, m_p);
+            else     accumulate_generic(pux, puy, puz);
+        }
+        // ---- (B) this sample ---------------------------------------------------------------------
+        double s0 = 0.0, c0 = 1.0;                      // tube 0 is pinned to 0 after the head step
+        if (HEAD) fast_sincos(al[0], s0, c0);
+        // section masks on the exact arc position (integer compares of the bit patterns)
         bool in_k[S], in_c[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            in_k[s] = (pos <= c.end[s]);
-            in_c[s] = in_k[s] && (pos >= c.start[s]);
+            in_k[s] = (s == S - 1) ? true : le_nonneg(pos, c.end[s]);   // pos <= ArcEnd = End_{S-1}
+            in_c[s] = in_k[s] && le_nonneg(c.start[s], pos);
         }
-        // 1 / (sum of stiffness of the sections that reach this position): End is
-        // non-decreasing in s, so the active set is always a suffix {s0..S-1}.
+        // 1 / (stiffness of the sections reaching this position): the active set is a suffix
         double rks = rb.rk[S - 1];
 #pragma unroll
         for (int s = S - 2; s >= 0; --s) rks = in_k[s] ? rb.rk[s] : rks;
 
         double cx = 0.0, cy = 0.0;
+        bool first = true;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const double g = in_c[s] ? rb.kg[s] : 0.0;
 #pragma unroll
             for (int j = 0; j < L::nt(s); ++j) {
                 const int t = L::t0(s) + j;
-                cx = x_fma(-sn[t], g, cx);
-                cy = x_fma(cs[t], g, cy);
+                const double st = (t == 0) ? s0 : sn[t];
+                const double ct = (t == 0) ? c0 : cs[t];
+                if (!HEAD && t == 0) { cy = g; first = false; continue; }   // sin 0 = 0, cos 0 = 1
+                if (first) { cx = -st * g; cy = ct * g; first = false; }
+                else       { cx = x_fma(-st, g, cx); cy = x_fma(ct, g, cy); }
             }
         }
         cx *= rks;
         cy *= rks;
         double uxs[T];
 #pragma unroll
-        for (int t = 0; t < T; ++t) uxs[t] = x_fma(cs[t], cx, sn[t] * cy);
-        const double uy_in = x_fma(cs[T - 1], cy, -(sn[T - 1] * cx));
-        const double uz_k  = uzs[T - 1];
+        for (int t = 0; t < T; ++t) {
+            if (t == 0) uxs[t] = HEAD ? x_fma(c0, cx, s0 * cy) : cx;
+            else        uxs[t] = x_fma(cs[t], cx, sn[t] * cy);
+        }
+        double uy_in;
+        if (T == 1) uy_in = HEAD ? x_fma(c0, cy, -(s0 * cx)) : cy;
+        else        uy_in = x_fma(cs[T - 1], cy, -(sn[T - 1] * cx));
+        const double uz_k = uzs[T - 1];
 
         double a_k = al[T - 1];
-        if (k >= 1) {
-            const double z0 = uzs[0];
+        if (!TAIL) {
+            // tube angles with the previous sample's torsion (section_i.h:289-312)
             al[0] = 0.0;
 #pragma unroll
-            for (int t = 1; t < T; ++t) al[t] = x_fma(h, uzs[t] - z0, al[t]);
+            for (int t = 1; t < T; ++t) al[t] = al[t] + dl[t];
             a_k = al[T - 1];
-            double cz = 0.0;
+            // torsion (section_i.h:243-286).  A section that does not reach this position yet
+            // still has u_z = 0 (its update is masked by in_c, and in_c implies in_k), so the
+            // in_k mask on the balance coefficients is redundant and dropped.
+            if (T > 1) {
+                double cz = 0.0;
 #pragma unroll
-            for (int t = T - 2; t >= 0; --t) {
-                const int s = L::sec_of(t);
-                const double cc = in_k[s] ? rb.czc[t] : 0.0;
-                const double hk = in_c[s] ? hko[t] : 0.0;
-                cz     = x_fma(cc, uzs[t], cz);
-                uzs[t] = x_fma(hk, uxs[t], uzs[t]);
+                for (int t = T - 2; t >= 0; --t) {
+                    const int s = L::sec_of(t);
+                    const double hk = in_c[s] ? hko[t] : 0.0;
+                    cz     = (t == T - 2) ? rb.czc[t] * uzs[t] : x_fma(rb.czc[t], uzs[t], cz);
+                    uzs[t] = x_fma(hk, uxs[t], uzs[t]);
+                }
+                uzs[T - 1] = -cz * rb.cl;
+            } else {
+                uzs[0] = 0.0;      // -0 * cl, section_i.h:285 with an empty balance
             }
-            uzs[T - 1] = -cz * rb.cl;
+            // sin/cos of the new angles, for the next sample
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                if (HOT && ROT) {
+                    const double d  = dl[t];
+                    const double d2 = d * d;
+                    double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
+                    double ps = x_fma(CTRK_FC.qb4[0], d2, CTRK_FC.qb4[1]);
+                    pc = x_fma(pc, d2, CTRK_FC.qa4[2]);
+                    ps = x_fma(ps, d2, CTRK_FC.qb4[2]);
+                    pc = x_fma(pc, d2, CTRK_FC.qa4[3]);
+                    ps = x_fma(ps, d2, CTRK_FC.qb4[3]);
+                    const double cd = x_fma(pc, d2, 1.0);          // cos d
+                    const double sd = x_fma(d * d2, ps, d);        // sin d
+                    const double s1 = x_fma(cs[t], sd, sn[t] * cd);
+                    const double c1 = x_fma(-sn[t], sd, cs[t] * cd);
+                    sn[t] = s1; cs[t] = c1;
+                } else if (HOT) {
+                    sincos_bounded(al[t], sn[t], cs[t]);
+                } else {
+                    fast_sincos(al[t], sn[t], cs[t]);
+                }
+            }
         }
         on_sample(k, uxs[T - 1], uy_in, uz_k, a_k);
-
-        if (tip && k <= tipk) {
-            double ew, ex, ey, ez, ex_p, ey_p, ez_p;
-            se3_step_fast(uxs[T - 1], uy_in, uz_k, h, rb.ztol, ew, ex, ey, ez, ex_p, ey_p, ez_p);
-            // translation: P.p <- pe + R(e) P.p   with R(e) v = v + 2 w (q x v) + 2 q x (q x v)
-            const double tx = 2.0 * x_fma(ey, Pz, -(ez * Py));
-            const double ty = 2.0 * x_fma(ez, Px, -(ex * Pz));
-            const double tz = 2.0 * x_fma(ex, Py, -(ey * Px));
-            const double nx = Px + ex_p, ny = Py + ey_p, nz = Pz + ez_p;
-            Px = x_fma(ew, tx, nx) + x_fma(ey, tz, -(ez * ty));
-            Py = x_fma(ew, ty, ny) + x_fma(ez, tx, -(ex * tz));
-            Pz = x_fma(ew, tz, nz) + x_fma(ex, ty, -(ey * tx));
-            // rotation: Q <- e (x) Q
-            const double w2 = x_fma(-ez, Qz, x_fma(-ey, Qy, x_fma(-ex, Qx, ew * Qw)));
-            const double x2 = x_fma(-ez, Qy, x_fma(ey, Qz, x_fma(ex, Qw, ew * Qx)));
-            const double y2 = x_fma(-ex, Qz, x_fma(ez, Qx, x_fma(ey, Qw, ew * Qy)));
-            const double z2 = x_fma(-ey, Qx, x_fma(ex, Qy, x_fma(ez, Qw, ew * Qz)));
-            Qw = w2; Qx = x2; Qy = y2; Qz = z2;
-            if (k == tipk) a_tip = a_k;
+        if (want_tip) {
+            if (TAIL) {
+                accumulate_generic(uxs[T - 1], uy_in, uz_k);
+            } else if (HEAD && k > c.nframes - 1) {
+                pux = puy = puz = 0.0;                  // dropped tip sample: pending = identity step
+            } else {
+                pux = uxs[T - 1]; puy = uy_in; puz = uz_k;
+            }
+            if (k == c.nframes - 1) a_tip = a_k;
         }
-        if (k >= 1) pos = x_sub(pos, h);
+        if (!TAIL) pos = x_sub(pos, c.h);
     }
-    if (tip) {
+
+    CTR_HD void run()
+    {
+        const int n = c.n;
+        double dl[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) dl[t] = 0.0;         // torsion is zero at the tip
+        if (n == 1) {
+            step<true, true, false>(0, dl, 0.0, 0.0);
+            return;
+        }
+        step<true, false, false>(n - 1, dl, 0.0, 0.0);
+#pragma unroll 1
+        for (int k = n - 2; k >= 1; --k) {
+            // top-of-iteration quantities shared by the hot tests and the hot steps
+            int dmax = 0, amax = 0;
+            const double z0 = uzs[0];
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                dl[t] = c.h * (uzs[t] - z0);
+                const int d = hi_word(dl[t]) & 0x7fffffff;
+                const int a = hi_word(al[t]) & 0x7fffffff;
+                dmax = d > dmax ? d : dmax;
+                amax = a > amax ? a : amax;
+            }
+            const double sxy = x_fma(puy, puy, pux * pux);
+            const double n2  = x_fma(puz, puz, sxy);
+            const double m   = n2 * kc.hh2;
+            const bool se3_hot = !want_tip || (le_nonneg(kc.ztol2, n2) && hi_word(m) < 0x3f700000);
+            const bool rot_ok  = dmax < 0x3fb00000;          // every |d_t| < 2^-4
+            const bool sc_ok   = amax < 0x408f0000;          // every |alpha_t| < 992 (+ |d_t| stays < 1024)
+#ifdef CTRK_COUNT_COLD   /* host-side analysis builds only (tests/hostsim) */
+            ++g_iter_total; if (!(se3_hot && (rot_ok || sc_ok))) ++g_iter_cold;
+            if (!rot_ok) ++g_iter_cold_delta;
+#endif
+            if (se3_hot && rot_ok)                 step<false, false, true, true>(k, dl, sxy, m);
+            else if (se3_hot && sc_ok && dmax < 0x40300000) step<false, false, true, false>(k, dl, sxy, m);
+            else                                   step<false, false, false>(k, dl, sxy, m);
+        }
+        {
+            const double z0 = uzs[0];
+#pragma unroll
+            for (int t = 1; t < T; ++t) dl[t] = c.h * (uzs[t] - z0);    // unused by the tail
+        }
+        step<false, true, false>(0, dl, 0.0, 0.0);
+    }
+};
+
+// WANT_TIP = false skips the frame product (backbone kernels build frames in their second pass).
+template <class L, bool WANT_TIP, class OnSample>
+CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* albase,
+                       OnSample on_sample)
+{
+    constexpr int T = L::T;
+    FastSweep<L, WANT_TIP, OnSample> sw(rb, c, on_sample);
+    sw.run();
+    if (WANT_TIP && tip) {
         // quaternion -> rotation (normalised: |Q| drifts by ~N ulp), then Init * Rz * P
+        const double Qw = sw.Qw, Qx = sw.Qx, Qy = sw.Qy, Qz = sw.Qz;
         const double nn = Qw * Qw + Qx * Qx + Qy * Qy + Qz * Qz;
         const double sc = 2.0 / nn;
         double Pm[12];
@@ -613,16 +903,17 @@ CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* a
         Pm[6] = sc * (Qx * Qz + Qw * Qy);
         Pm[7] = sc * (Qy * Qz - Qw * Qx);
         Pm[8] = 1.0 - sc * (Qx * Qx + Qy * Qy);
-        Pm[9] = Px; Pm[10] = Py; Pm[11] = Pz;
+        Pm[9] = sw.Px; Pm[10] = sw.Py; Pm[11] = sw.Pz;
         double sa, ca;
-        fast_sincos(a_tip + c.theta, sa, ca);
+        fast_sincos(sw.a_tip + c.theta, sa, ca);
         tf_finish(rb.ini, Pm, sa, ca, tip);
     }
     if (albase) {
 #pragma unroll
-        for (int t = 0; t < T; ++t) albase[t] = al[t];
+        for (int t = 0; t < T; ++t) albase[t] = sw.al[t];
     }
 }
+
 
 // robot_i.h:1286-1307: outer radius of the section covering each sample.  Writes radius[0..n)
 // with stride `stride` doubles.

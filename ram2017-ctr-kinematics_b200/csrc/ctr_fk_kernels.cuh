@@ -60,8 +60,11 @@ __device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg)
 }
 
 // ---- tip-only kernel ---------------------------------------------------------------------------
+// Register budget: 4 CTAs of 128 threads per SM (16 warps) leaves 128 registers per thread.  Measured
+// on B200 (tools/tune_tip.cu): capping registers for 20 or 24 warps/SM is 3-5 % slower — the sweep
+// is bound by FP64 issue, not by latency that more warps could hide.
 template <class L, bool FAST>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, FAST ? 4 : 1)
 fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -76,7 +79,7 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
 
     double tip[12];
     double alb[L::T];
-    if (FAST) solve_fast<L>(rb, c, a.tip ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
+    if (FAST) solve_fast<L, true>(rb, c, tip, a.alpha_base ? alb : nullptr, NoSample{});
     else      solve_strict<L, true>(rb, c, a.tip ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
 
     if (a.tip) store_tf(a.tip + cfg * 12, tip);
@@ -128,7 +131,7 @@ fk_backbone_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Fk
     else       { park.base = a.backbone + cfg * 12 * (int64_t)rb.maxs; park.kstride = 12; park.cstride = 1; }
 
     double alb[L::T];
-    if (FAST) solve_fast<L>(rb, c, nullptr, alb, park);
+    if (FAST) solve_fast<L, false>(rb, c, nullptr, alb, park);
     else      solve_strict<L, false>(rb, c, nullptr, alb, park);
 
     double I[12], F[12];

@@ -43,7 +43,7 @@ fk_jacobian_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Ja
         return;
     }
     double tip0[12];
-    solve_fast<L>(rb, c, tip0, nullptr, NoSample{});
+    solve_fast<L, true>(rb, c, tip0, nullptr, NoSample{});
     if (a.tip) store_tf(a.tip + cfg * 12, tip0);
 
     // column 2 (alpha of tube 0) is zero (robot_i.h:928)
@@ -78,7 +78,7 @@ fk_jacobian_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Ja
             for (int e = 0; e < 6; ++e) col[e] = qnan;
         } else {
             double tp[12];
-            solve_fast<L>(rb, cp, tp, nullptr, NoSample{});
+            solve_fast<L, true>(rb, cp, tp, nullptr, NoSample{});
             jac_column(tip0, tp, dq, col);
         }
 #pragma unroll

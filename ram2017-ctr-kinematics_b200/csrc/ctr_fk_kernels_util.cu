@@ -10,14 +10,19 @@ namespace ctrk {
 // In step mode N_c = floor(sum(Phi)/step) differs per configuration (1..MaxSamples).  A warp runs
 // as long as its longest sweep, so configurations are counting-sorted by N_c (longest first) and
 // the solver threads pick their configuration through `order`.  Only the 4-byte index moves.
+//
+// Both passes keep a block-private histogram in shared memory (one CTA covers kBinItems
+// configurations) and touch the global bins once per CTA and bin: with one global atomic per
+// configuration the ~256 hot addresses serialise in L2 (measured: 213 us per pass for 1M
+// configurations, 17 % of the whole step; now a few us).
+constexpr int kBinThreads = 256;
+constexpr int kBinPerThread = 16;
+constexpr int kBinItems = kBinThreads * kBinPerThread;
+
 template <class L>
-__global__ void __launch_bounds__(256)
-count_samples_kernel(const __grid_constant__ KRobot rb, const double* __restrict__ jv, int64_t B,
-                     int mode, double step, int nsamples, int32_t* __restrict__ n,
-                     uint32_t* __restrict__ hist)
+__device__ __forceinline__ int sample_count_of(const KRobot& rb, const double* __restrict__ jv, int64_t i,
+                                               int mode, double step, int nsamples)
 {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= B) return;
     double q[L::NJ];
     load_jv<L>(jv, i, q);
     // Only N is needed for the ordering (not nframes): skip the position replay.
@@ -29,52 +34,97 @@ count_samples_kernel(const __grid_constant__ KRobot rb, const double* __restrict
         if (!((phi >= 0.0) && (phi <= rb.len[s]))) bad = true;
         run = x_add(run, phi);
     }
-    int cnt = 0;
-    if (!bad) {
-        if (mode == 0) {
-            const double qd = x_div(run, step);
-            cnt = (qd >= (double)rb.maxs + 1.0) ? rb.maxs + 1 : (int)qd;
-            if (cnt < 1) cnt = 1;
-            if (cnt > rb.maxs) cnt = rb.maxs;
-        } else {
-            cnt = nsamples < rb.maxs ? nsamples : rb.maxs;
+    if (bad) return 0;
+    if (mode != 0) return nsamples < rb.maxs ? nsamples : rb.maxs;
+    const double qd = x_div(run, step);
+    int cnt = (qd >= (double)rb.maxs + 1.0) ? rb.maxs + 1 : (int)qd;
+    if (cnt < 1) cnt = 1;
+    if (cnt > rb.maxs) cnt = rb.maxs;
+    return cnt;
+}
+
+template <class L>
+__global__ void __launch_bounds__(kBinThreads)
+count_samples_kernel(const __grid_constant__ KRobot rb, const double* __restrict__ jv, int64_t B,
+                     int mode, double step, int nsamples, int32_t* __restrict__ n,
+                     uint32_t* __restrict__ hist, int nbins)
+{
+    extern __shared__ uint32_t sh[];
+    for (int b = threadIdx.x; b < nbins; b += kBinThreads) sh[b] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kBinItems;
+#pragma unroll 4
+    for (int j = 0; j < kBinPerThread; ++j) {
+        const int64_t i = base + (int64_t)j * kBinThreads + threadIdx.x;    // coalesced n[] stores
+        if (i < B) {
+            const int cnt = sample_count_of<L>(rb, jv, i, mode, step, nsamples);
+            n[i] = cnt;
+            atomicAdd(&sh[cnt], 1u);
         }
     }
-    n[i] = cnt;
-    atomicAdd(&hist[cnt], 1u);   // ptxas aggregates same-address atomics of a warp
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += kBinThreads)
+        if (sh[b]) atomicAdd(&hist[b], sh[b]);
 }
 
 // hist[0..nbins) -> start offset of each bin when bins are laid out from the LARGEST count down.
 __global__ void bin_offsets_kernel(uint32_t* hist, int nbins)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint32_t acc = 0;
-    for (int b = nbins - 1; b >= 0; --b) {
-        const uint32_t c = hist[b];
-        hist[b] = acc;
-        acc += c;
+    extern __shared__ uint32_t sh[];
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = hist[b];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = nbins - 1; b >= 0; --b) {
+            const uint32_t c = sh[b];
+            sh[b] = acc;
+            acc += c;
+        }
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) hist[b] = sh[b];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBinThreads)
 bin_scatter_kernel(const int32_t* __restrict__ n, int64_t B, uint32_t* __restrict__ cursor,
-                   int32_t* __restrict__ order)
+                   int32_t* __restrict__ order, int nbins)
 {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= B) return;
-    const uint32_t slot = atomicAdd(&cursor[n[i]], 1u);
-    order[slot] = (int32_t)i;
+    extern __shared__ uint32_t sh[];          // [0,nbins): block histogram, then the block's base
+    uint32_t* fill = sh + nbins;              // [nbins, 2 nbins): running rank inside the block
+    for (int b = threadIdx.x; b < 2 * nbins; b += kBinThreads) sh[b] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kBinItems;
+    int cnt[kBinPerThread];
+#pragma unroll
+    for (int j = 0; j < kBinPerThread; ++j) {
+        const int64_t i = base + (int64_t)j * kBinThreads + threadIdx.x;
+        cnt[j] = (i < B) ? n[i] : -1;
+        if (cnt[j] >= 0) atomicAdd(&sh[cnt[j]], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += kBinThreads)
+        if (sh[b]) sh[b] = atomicAdd(&cursor[b], sh[b]);      // reserve a contiguous run per bin
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kBinPerThread; ++j) {
+        if (cnt[j] < 0) continue;
+        const int64_t i = base + (int64_t)j * kBinThreads + threadIdx.x;
+        const uint32_t r = atomicAdd(&fill[cnt[j]], 1u);
+        order[sh[cnt[j]] + r] = (int32_t)i;
+    }
 }
 
 cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, int64_t B, int mode,
                                  double step, int nsamples, int32_t* n, uint32_t* hist, cudaStream_t st)
 {
     if (B <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((B + 255) / 256);
+    const unsigned grid = (unsigned)((B + kBinItems - 1) / kBinItems);
+    const int nbins = rb.maxs + 2;
+    const size_t smem = sizeof(uint32_t) * (size_t)nbins;
     switch (key) {
 #define X(S, A, Bq, C) \
     case S * 1000 + A * 100 + Bq * 10 + C: \
-        count_samples_kernel<Lay<S, A, Bq, C>><<<grid, 256, 0, st>>>(rb, jv, B, mode, step, nsamples, n, hist); \
+        count_samples_kernel<Lay<S, A, Bq, C>><<<grid, kBinThreads, smem, st>>>(rb, jv, B, mode, step, nsamples, n, hist, nbins); \
         break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X
@@ -86,15 +136,15 @@ cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, in
 
 cudaError_t launch_bin_offsets(uint32_t* hist, int nbins, cudaStream_t st)
 {
-    bin_offsets_kernel<<<1, 32, 0, st>>>(hist, nbins);
+    bin_offsets_kernel<<<1, 256, sizeof(uint32_t) * (size_t)nbins, st>>>(hist, nbins);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, cudaStream_t st)
+cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, int nbins, cudaStream_t st)
 {
     if (B <= 0) return cudaSuccess;
-    bin_scatter_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(n, B, cursor, order);
+    bin_scatter_kernel<<<(unsigned)((B + kBinItems - 1) / kBinItems), kBinThreads, 2 * sizeof(uint32_t) * (size_t)nbins, st>>>(n, B, cursor, order, nbins);
     count_launch();
     return cudaGetLastError();
 }

@@ -53,7 +53,7 @@ cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStr
 cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, int64_t B, int mode,
                                  double step, int nsamples, int32_t* n, uint32_t* hist, cudaStream_t st);
 cudaError_t launch_bin_offsets(uint32_t* hist, int nbins, cudaStream_t st);   // in place: descending exclusive scan
-cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, cudaStream_t st);
+cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, int nbins, cudaStream_t st);
 
 struct SamplerArgs {
     uint64_t seed;

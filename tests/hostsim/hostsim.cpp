@@ -32,7 +32,7 @@ void run(const KRobot& rb, const double* jv, int64_t B, int mode, double step, i
         if (c.status) continue;
         Park park{samples ? samples + i * 4 * (int64_t)rb.maxs : nullptr};
         double t[12], ab[L::T];
-        if (fast) solve_fast<L>(rb, c, t, ab, park);
+        if (fast) solve_fast<L, true>(rb, c, t, ab, park);
         else      solve_strict<L, true>(rb, c, t, ab, park);
         if (tip) std::memcpy(tip + 12 * i, t, sizeof t);
         if (alpha_base) std::memcpy(alpha_base + L::T * i, ab, sizeof ab);
