@@ -119,6 +119,15 @@ def visible_index(local_rank):
     return local_rank
 
 
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1; the oracle takes
+    an explicit thread count (num_threads clause), so that default does not cap the CPU arm."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(desc, a, nthreads, sample, seed, repeat=1):
     """Times the CPU oracle (a restatement of the reference FK; the reference itself cannot be
     built here) on `sample` configurations of the bench workload."""
@@ -145,7 +154,7 @@ def run_reference(a):
     import ctrfk
     import oracle_lib
     desc = ctrfk.desc_from_xml(ctrfk.resource(a.robot), 256)
-    threads = oracle_lib.max_threads()
+    threads = host_threads()
     seed = 20171
     # bounded sample per step: ~1 s of CPU work, so K+W steps end within minutes
     probe_rate, _ = cpu_reference_rate(desc, a, threads, 4096, seed)
@@ -333,8 +342,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ---------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        import oracle_lib
-        threads = oracle_lib.max_threads()
+        threads = host_threads()
         r1, _ = cpu_reference_rate(desc, a, 1, 2048, seed)
         sample = a.cpu_sample or int(min(B, max(20000, r1 * threads * 10.0)))      # ~10 s of CPU work
         rate, secs = cpu_reference_rate(desc, a, threads, sample, seed)
