@@ -293,14 +293,35 @@ def main():
             traffic = json.load(open(prof_json)).get(("backbone" if a.backbone else "tip") + "_" + a.mode)
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / peak_tflops if peak_tflops > 0 else None, "traffic": traffic,
-                "kernel_ms": kern_ms,
-                "alg_flops_per_launch": alg_flops,
-                "alg_bytes_per_launch": B * (njv * 8 + 96 + ((12 + 1) * 8 * nsum / B if a.backbone else 0)),
-                "peak_source": "measured live: independent-DFMA-chain probe on all SMs (ctr_fk_fp64_probe); "
-                               "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
-                "alg_flops_per_sample_step": fstep, "mean_samples": nsum / B}
+    if a.backbone:
+        # config 4: 104 B of frames + radius per sample — HBM-store bound
+        hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+        try:
+            hbm_peak = float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+        alg_bytes = B * (njv * 8 + 96) + (12 + 1) * 8 * nsum
+        gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": traffic, "kernel_ms": kern_ms, "alg_bytes_per_launch": alg_bytes,
+                    "peak_source": hbm_src, "mean_samples": nsum / B,
+                    "fp64": {"achieved_tflops": achieved, "peak_tflops": peak_tflops}}
+    else:
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tflops if peak_tflops > 0 else None, "traffic": traffic,
+                    "kernel_ms": kern_ms,
+                    "alg_flops_per_launch": alg_flops,
+                    "alg_bytes_per_launch": B * (njv * 8 + 96),
+                    "peak_source": "measured live: independent-DFMA-chain probe on all SMs (ctr_fk_fp64_probe); "
+                                   "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
+                    "alg_flops_per_sample_step": fstep, "mean_samples": nsum / B}
+
+    if a.f32:
+        # the FP32 variant runs on the FP32 FMA pipe; no FP32 peak is measured here, so no fraction
+        roofline.update({"bound": "fp32", "peak": None, "frac": None,
+                         "peak_source": "not measured (FP32 variant is not the headline); achieved counts the "
+                                        "reference's algorithmic flops"})
 
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers) --------------------
     h_jv = torch.empty(B, njv, dtype=torch.float64).pin_memory()

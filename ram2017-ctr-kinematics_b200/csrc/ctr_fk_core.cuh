@@ -52,6 +52,7 @@ struct KRobot {
     double rk[kMaxSec];      // 1 / (ksum[s] + ... + ksum[S-1])       (FAST)
     double onu_last;         // 1 + nu of the innermost tube          (section_i.h:285)
     double cl;               // onu_last / ksum[S-1]                  (FAST)
+    double qini[4];          // unit quaternion (w,x,y,z) of the entry frame's rotation
     double ztol;
     int    maxs;
     int    nsec;
@@ -914,6 +915,68 @@ CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* a
     }
 }
 
+
+// ---- rigid transform as (unit quaternion, translation): used by the warp-parallel backbone pass
+struct QT {
+    double w, x, y, z, px, py, pz;
+};
+CTR_HD QT qt_identity()
+{
+    QT t; t.w = 1.0; t.x = t.y = t.z = 0.0; t.px = t.py = t.pz = 0.0;
+    return t;
+}
+// a * b : rotation a.q (x) b.q, translation a.p + R(a.q) b.p
+CTR_HD QT qt_mul(const QT& a, const QT& b)
+{
+    QT r;
+    const double tx = x_fma(a.y, b.pz, -(a.z * b.py));
+    const double ty = x_fma(a.z, b.px, -(a.x * b.pz));
+    const double tz = x_fma(a.x, b.py, -(a.y * b.px));
+    const double ix = x_fma(a.w, tx, x_fma(a.y, tz, -(a.z * ty)));
+    const double iy = x_fma(a.w, ty, x_fma(a.z, tx, -(a.x * tz)));
+    const double iz = x_fma(a.w, tz, x_fma(a.x, ty, -(a.y * tx)));
+    r.px = x_fma(2.0, ix, a.px + b.px);
+    r.py = x_fma(2.0, iy, a.py + b.py);
+    r.pz = x_fma(2.0, iz, a.pz + b.pz);
+    r.w = x_fma(-a.z, b.z, x_fma(-a.y, b.y, x_fma(-a.x, b.x, a.w * b.w)));
+    r.x = x_fma(-a.z, b.y, x_fma(a.y, b.z, x_fma(a.x, b.w, a.w * b.x)));
+    r.y = x_fma(-a.x, b.z, x_fma(a.z, b.x, x_fma(a.y, b.w, a.w * b.y)));
+    r.z = x_fma(-a.y, b.x, x_fma(a.x, b.y, x_fma(a.z, b.w, a.w * b.z)));
+    return r;
+}
+// Frame_k = Init * Rz(ang) * I  (robot_i.h:714-716) with the rotations composed as quaternions.
+// (sh, ch) = sin/cos(ang/2).  Output column-major 3x4.
+CTR_HD void qt_frame(const KRobot& rb, const QT& I, double sh, double ch, double* f)
+{
+    // q1 = q_init (x) q_z(ang/2)
+    const double w1 = x_fma(-rb.qini[3], sh, rb.qini[0] * ch);
+    const double x1 = x_fma(rb.qini[2], sh, rb.qini[1] * ch);
+    const double y1 = x_fma(-rb.qini[1], sh, rb.qini[2] * ch);
+    const double z1 = x_fma(rb.qini[0], sh, rb.qini[3] * ch);
+    // q = q1 (x) I.q
+    const double w = x_fma(-z1, I.z, x_fma(-y1, I.y, x_fma(-x1, I.x, w1 * I.w)));
+    const double x = x_fma(-z1, I.y, x_fma(y1, I.z, x_fma(x1, I.w, w1 * I.x)));
+    const double y = x_fma(-x1, I.z, x_fma(z1, I.x, x_fma(y1, I.w, w1 * I.y)));
+    const double z = x_fma(-y1, I.x, x_fma(x1, I.y, x_fma(z1, I.w, w1 * I.z)));
+    const double x2 = x + x, y2 = y + y, z2 = z + z;
+    f[0] = 1.0 - x_fma(y2, y, z2 * z);
+    f[1] = x_fma(x2, y, w * z2);
+    f[2] = x_fma(x2, z, -(w * y2));
+    f[3] = x_fma(x2, y, -(w * z2));
+    f[4] = 1.0 - x_fma(x2, x, z2 * z);
+    f[5] = x_fma(y2, z, w * x2);
+    f[6] = x_fma(x2, z, w * y2);
+    f[7] = x_fma(y2, z, -(w * x2));
+    f[8] = 1.0 - x_fma(x2, x, y2 * y);
+    // translation: p_init + R_init (Rz(ang) I.p);  sin/cos(ang) from the half angle
+    const double sa = 2.0 * sh * ch, ca = x_fma(ch, ch, -(sh * sh));
+    const double rx = x_fma(ca, I.px, -(sa * I.py));
+    const double ry = x_fma(ca, I.py, sa * I.px);
+    const double rz = I.pz;
+    f[9]  = x_fma(rb.ini[0], rx, x_fma(rb.ini[3], ry, x_fma(rb.ini[6], rz, rb.ini[9])));
+    f[10] = x_fma(rb.ini[1], rx, x_fma(rb.ini[4], ry, x_fma(rb.ini[7], rz, rb.ini[10])));
+    f[11] = x_fma(rb.ini[2], rx, x_fma(rb.ini[5], ry, x_fma(rb.ini[8], rz, rb.ini[11])));
+}
 
 // robot_i.h:1286-1307: outer radius of the section covering each sample.  Writes radius[0..n)
 // with stride `stride` doubles.

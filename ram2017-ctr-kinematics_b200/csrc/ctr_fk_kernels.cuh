@@ -168,6 +168,209 @@ fk_backbone_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Fk
     if (a.status) a.status[cfg] = 0;
 }
 
+// ---- backbone kernel, AoS layout, FAST arithmetic: warp-parallel second pass ---------------------
+// The thread-per-configuration second pass above stores each frame 24.5 KB away from its warp
+// neighbours' frames and reads the parked samples with one dependent load per step (ncu, round 1:
+// 12.9 GB of DRAM traffic for 5.3 GB of output, long-scoreboard stalls dominate).  Here:
+//   pass 1  one thread per configuration sweeps tip -> base and parks (u_x,u_y,u_z,alpha) of every
+//           sample COMPACTLY at the start of the configuration's own output region
+//           ([k][4] doubles = n*32 B contiguous, 32-B aligned full-sector stores);
+//   pass 2  each warp takes the CTA's configurations one at a time: the n*32 B block is copied to
+//           shared memory with cp.async (16 B per lane per request, all requests in flight at
+//           once, double-buffered so the next configuration's block streams in while this one is
+//           processed); lane l owns the contiguous samples [l*c, (l+1)*c), c = ceil(n/32).  The
+//           running product I_k = E_0 ... E_k is a prefix "sum" over SE(3) composition, computed
+//           as lane-local products + a warp scan (5 shuffle rounds) + a second lane-local walk that
+//           emits Frame_k = Init Rz(alpha_k+theta) I_k.  A warp writes one configuration's n*96 B
+//           contiguously.  Transforms travel as (unit quaternion, translation): 7 doubles per
+//           shuffle, 37 FP64 instructions per composition.
+// Shared memory: kBbWarps warps x 2 buffers x MaxSamples x 32 B (32 KB per CTA at MaxSamples=256).
+constexpr int kBbWarps = 2;
+constexpr int kBbBufs = 1;              // staging buffers per warp (2 = prefetch the next block)
+constexpr int kBbBlock = kBbWarps * 32;
+constexpr int kBbMaxSamples = 1024;     // larger robots use the thread-per-configuration kernel
+
+struct BbShared {
+    double  h, theta;
+    double  end[kMaxSec];
+    int64_t cfg;
+    int     nframes;
+    int     ok;
+};
+
+__device__ __forceinline__ QT qt_shfl_up(const QT& t, int off)
+{
+    QT r;
+    r.w = __shfl_up_sync(0xffffffffu, t.w, off);   r.x = __shfl_up_sync(0xffffffffu, t.x, off);
+    r.y = __shfl_up_sync(0xffffffffu, t.y, off);   r.z = __shfl_up_sync(0xffffffffu, t.z, off);
+    r.px = __shfl_up_sync(0xffffffffu, t.px, off); r.py = __shfl_up_sync(0xffffffffu, t.py, off);
+    r.pz = __shfl_up_sync(0xffffffffu, t.pz, off);
+    return r;
+}
+
+// One 256-bit store (sm_100: STG.E.ENL2.256): a full 32-B sector per request.  These kernels are
+// bound by the number of L2 write requests their scattered stores generate, not by bytes
+// (ncu: long-scoreboard stalls on registers still owned by in-flight 16-B stores), so every store
+// here carries a whole sector.  `p` must be 32-B aligned.
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void store_tf256(double* dst, const double* t)
+{
+    st256(dst, t[0], t[1], t[2], t[3]);
+    st256(dst + 4, t[4], t[5], t[6], t[7]);
+    st256(dst + 8, t[8], t[9], t[10], t[11]);
+}
+
+// parks a sample as one 32-B store
+struct ParkCompact {
+    double* base;
+    __device__ __forceinline__ void operator()(int k, double ux, double uy, double uz, double al) const
+    {
+        st256(base + 4 * (int64_t)k, ux, uy, uz, al);
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <class L>
+__global__ void __launch_bounds__(kBbBlock)
+fk_backbone_warp_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
+{
+    extern __shared__ __align__(16) double sh_park[];       // [kBbWarps][2][maxs*4]
+    __shared__ BbShared sh[kBbBlock];
+    const int64_t i = (int64_t)blockIdx.x * kBbBlock + threadIdx.x;
+    BbShared me;
+    me.ok = 0; me.nframes = 0; me.cfg = 0; me.h = 0.0; me.theta = 0.0;
+#pragma unroll
+    for (int s = 0; s < kMaxSec; ++s) me.end[s] = 0.0;
+
+    // ---- pass 1: one thread per configuration, tip -> base sweep, samples parked in place -----
+    if (i < a.B) {
+        const int64_t cfg = a.order ? (int64_t)a.order[i] : i;
+        double q[L::NJ];
+        load_jv<L>(a.jv, cfg, q);
+        Ctl<L> c;
+        setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
+        if (c.status) {
+            write_invalid<L>(a, cfg);
+        } else {
+            ParkCompact park;
+            park.base = a.backbone + cfg * 12 * (int64_t)rb.maxs;
+            double alb[L::T];
+            solve_fast<L, false>(rb, c, nullptr, alb, park);
+            if (a.n_out) a.n_out[cfg] = c.nframes;
+            if (a.step_out) a.step_out[cfg] = c.h;
+            if (a.alpha_base) {
+#pragma unroll
+                for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = alb[t];
+            }
+            if (a.status) a.status[cfg] = 0;
+            me.ok = 1; me.nframes = c.nframes; me.cfg = cfg; me.h = c.h; me.theta = c.theta;
+#pragma unroll
+            for (int s = 0; s < L::S; ++s) me.end[s] = c.end[s];
+        }
+    }
+    sh[threadIdx.x] = me;
+    __syncthreads();        // parked samples (global) and sh[] are visible to the whole CTA
+
+    // ---- pass 2: one warp per configuration ---------------------------------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* buf0 = sh_park + (size_t)warp * kBbBufs * 4 * rb.maxs;
+    auto prefetch = [&](int j, int which) {
+        const BbShared& cf = sh[warp * 32 + j];
+        if (cf.ok) {
+            const char* src = reinterpret_cast<const char*>(a.backbone + cf.cfg * 12 * (int64_t)rb.maxs);
+            char* dst = reinterpret_cast<char*>(buf0 + (size_t)which * 4 * rb.maxs);
+            const int bytes = cf.nframes * 32;
+            for (int o = lane * 16; o < bytes; o += 32 * 16) cp_async16(dst + o, src + o);
+        }
+        cp_async_commit();
+    };
+    if (kBbBufs == 2) prefetch(0, 0);
+    for (int j = 0; j < 32; ++j) {
+        if (kBbBufs == 2) {
+            if (j + 1 < 32) prefetch(j + 1, (j + 1) & 1);  // stream the next block in meanwhile
+            else            cp_async_commit();
+            cp_async_wait<1>();                             // this configuration's block has landed
+        } else {
+            prefetch(j, 0);
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const BbShared& cf = sh[warp * 32 + j];
+        if (cf.ok) {                                        // warp-uniform
+            const int n   = cf.nframes;
+            const int cnt = (n + 31) >> 5;
+            const int k0  = lane * cnt;
+            const int k1  = (k0 + cnt < n) ? k0 + cnt : n;
+            const double* pk = buf0 + (size_t)(kBbBufs == 2 ? (j & 1) : 0) * 4 * rb.maxs;
+            double* slot0 = a.backbone + cf.cfg * 12 * (int64_t)rb.maxs;
+            const StepConsts kc = make_step_consts(cf.h, rb.ztol);
+
+            QT T = qt_identity();
+            for (int k = k0; k < k1; ++k) {
+                const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
+                const double  uz = pk[4 * k + 2];
+                QT E;
+                se3_step_fast_k(v0.x, v0.y, uz, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
+                T = qt_mul(T, E);
+            }
+            // inclusive scan over lanes: T_l <- T_0 * ... * T_l
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const QT o = qt_shfl_up(T, off);
+                if (lane >= off) T = qt_mul(o, T);
+            }
+            QT I = qt_shfl_up(T, 1);
+            if (lane == 0) I = qt_identity();
+            {   // renormalise the carried rotation (|q| drifts by ~n ulp)
+                const double inv = rsqrt(I.w * I.w + I.x * I.x + I.y * I.y + I.z * I.z);
+                I.w *= inv; I.x *= inv; I.y *= inv; I.z *= inv;
+            }
+            for (int k = k0; k < k1; ++k) {
+                const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
+                const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);   // (u_z, alpha_k)
+                QT E;
+                se3_step_fast_k(v0.x, v0.y, v1.x, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
+                I = qt_mul(I, E);
+                double shf, chf, F[12];
+                fast_sincos(0.5 * (v1.y + cf.theta), shf, chf);
+                qt_frame(rb, I, shf, chf, F);
+                store_tf256(slot0 + (int64_t)k * 12, F);
+                if (k == n - 1 && a.tip) store_tf(a.tip + cf.cfg * 12, F);
+            }
+            if (a.radius) {
+                // robot_i.h:1286-1307, lanes striding over the samples of each section's run
+                double* rad = a.radius + cf.cfg * (int64_t)rb.maxs;
+                int    begin = 0;
+                double rsec  = 0.0;
+#pragma unroll
+                for (int s = 0; s < L::S; ++s) {
+                    if (begin >= n) continue;
+                    rsec = rb.rad[s];
+                    const double qd = x_div(cf.end[s], cf.h);
+                    int stop = (qd >= 0.0 && qd < (double)n) ? (int)qd : n;
+                    if (stop < begin) stop = begin;
+                    for (int k = begin + lane; k < stop; k += 32) rad[k] = rsec;
+                    begin = stop;
+                }
+                __syncwarp();
+                if (lane == 0 && n > 0) rad[n - 1] = rsec;
+            }
+        }
+        __syncwarp();       // everyone is done with this buffer before it is refilled
+    }
+}
+
 #define CTRK_LAUNCH_CASE(KERNEL, FASTV, S, A, Bq, C)                                              \
     case S * 1000 + A * 100 + Bq * 10 + C:                                                        \
         KERNEL<Lay<S, A, Bq, C>, FASTV><<<grid, kBlock, 0, st>>>(rb, a);                          \

@@ -25,6 +25,25 @@ cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cud
 {
     if (a.B <= 0) return cudaSuccess;
     const unsigned grid = grid_for(a.B);
+    // AoS: warp-parallel second pass (needs a 32-B aligned buffer for its 256-bit stores)
+    if (!a.soa && rb.maxs <= kBbMaxSamples && (reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0) {
+        const unsigned gridw = (unsigned)((a.B + kBbBlock - 1) / kBbBlock);
+        const size_t smem = sizeof(double) * 4 * (size_t)rb.maxs * kBbBufs * kBbWarps;
+        switch (key) {
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: { \
+        /* per device and cheap: set on every launch (above the 48 KB default for MaxSamples > 384) */ \
+        cudaError_t ea = cudaFuncSetAttribute(fk_backbone_warp_kernel<Lay<S, A, Bq, C>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (ea != cudaSuccess) return ea; \
+        fk_backbone_warp_kernel<Lay<S, A, Bq, C>><<<gridw, kBbBlock, smem, st>>>(rb, a); \
+        break; }
+            CTRK_FOR_EACH_LAYOUT_K(X)
+#undef X
+            default: return cudaErrorInvalidValue;
+        }
+        count_launch();
+        return cudaGetLastError();
+    }
     switch (key) {
 #define X(S, A, Bq, C) CTRK_LAUNCH_CASE(fk_backbone_kernel, true, S, A, Bq, C)
         CTRK_FOR_EACH_LAYOUT_K(X)

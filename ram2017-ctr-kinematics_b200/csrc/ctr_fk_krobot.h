@@ -69,6 +69,27 @@ inline int make_krobot(const ctr_robot_desc* d, KRobot* r)
             r->czc[t] = r->share[s] / r->onu[t];
         }
     }
+    {   // rotation matrix (column-major) -> unit quaternion, Shepperd's method
+        const double* R = r->ini;
+        const double m00 = R[0], m10 = R[1], m20 = R[2], m01 = R[3], m11 = R[4], m21 = R[5], m02 = R[6], m12 = R[7], m22 = R[8];
+        const double tr = m00 + m11 + m22;
+        double w, x, y, z;
+        if (tr > 0.0) {
+            const double s4 = 2.0 * std::sqrt(tr + 1.0);
+            w = 0.25 * s4; x = (m21 - m12) / s4; y = (m02 - m20) / s4; z = (m10 - m01) / s4;
+        } else if (m00 > m11 && m00 > m22) {
+            const double s4 = 2.0 * std::sqrt(1.0 + m00 - m11 - m22);
+            w = (m21 - m12) / s4; x = 0.25 * s4; y = (m01 + m10) / s4; z = (m02 + m20) / s4;
+        } else if (m11 > m22) {
+            const double s4 = 2.0 * std::sqrt(1.0 + m11 - m00 - m22);
+            w = (m02 - m20) / s4; x = (m01 + m10) / s4; y = 0.25 * s4; z = (m12 + m21) / s4;
+        } else {
+            const double s4 = 2.0 * std::sqrt(1.0 + m22 - m00 - m11);
+            w = (m10 - m01) / s4; x = (m02 + m20) / s4; y = (m12 + m21) / s4; z = 0.25 * s4;
+        }
+        const double nrm = std::sqrt(w * w + x * x + y * y + z * z);
+        r->qini[0] = w / nrm; r->qini[1] = x / nrm; r->qini[2] = y / nrm; r->qini[3] = z / nrm;
+    }
     const ctr_section_desc& last = d->sec[S - 1];
     r->onu_last = 1.0 + last.poisson[last.ntube - 1];
     r->cl       = r->onu_last / r->ksum[S - 1];

@@ -7,6 +7,7 @@
 
 #include "../../include/ctr_fk.h"
 #include "../../ram2017-ctr-kinematics_b200/csrc/ctr_fk_krobot.h"
+#include "../../ram2017-ctr-kinematics_b200/csrc/ctr_fk_core_f32.cuh"
 
 using namespace ctrk;
 
@@ -32,8 +33,11 @@ void run(const KRobot& rb, const double* jv, int64_t B, int mode, double step, i
         if (c.status) continue;
         Park park{samples ? samples + i * 4 * (int64_t)rb.maxs : nullptr};
         double t[12], ab[L::T];
-        if (fast) solve_fast<L, true>(rb, c, t, ab, park);
-        else      solve_strict<L, true>(rb, c, t, ab, park);
+        if (fast == 2) {       // FP32 variant (no alpha_base / samples)
+            solve_f32<L>(rb, c, t);
+            for (int q = 0; q < L::T; ++q) ab[q] = 0.0;
+        } else if (fast) solve_fast<L, true>(rb, c, t, ab, park);
+        else             solve_strict<L, true>(rb, c, t, ab, park);
         if (tip) std::memcpy(tip + 12 * i, t, sizeof t);
         if (alpha_base) std::memcpy(alpha_base + L::T * i, ab, sizeof ab);
     }
