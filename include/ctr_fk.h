@@ -18,6 +18,8 @@
  *     -> ctr_robot_desc (same fields, InitTrafo column-major).
  *   - calcJacobian (finite differences, NSamples form)                  robot_i.h:917-960
  *     -> ctr_fk_jacobian_batch.
+ *   - calcStability / calcDegreeStability                               robot_i.h:756-899
+ *     -> ctr_fk_stability_batch.
  *   - getRandomJointValues                                              robot_i.h:1308-1317,
  *                                                                       section_i.h:328-337
  *     -> ctr_fk_sample_joints (counter-based instead of mt19937; same distribution).
@@ -167,6 +169,19 @@ int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t 
 /* The same with HOST pointers (synchronous; staged through the device). */
 int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples,
                          double fd_trans, double fd_rot, double* jac, double* tip);
+
+/* Batched calcStability / calcDegreeStability (robot_i.h:756-818, :819-899), DEVICE pointers.
+ * For every tube 1..T-1 the tip angle is scanned in `angle_step` increments from 0 to its joint
+ * value (or from the joint value to 2*pi when it exceeds pi); each scan point runs the tip->base
+ * sweep (step mode, `arc_step`) and the configuration is unstable as soon as the tube's base
+ * angle decreases between two scan points.  JV[0] is ignored (set to 0, robot_i.h:762).
+ *   stable [B]  out, nullable: 1 stable, 0 unstable, -1 invalid joint values
+ *   degree [B]  out, nullable: calcDegreeStability's return value, atan2(angle_step, smallest
+ *               base-angle increment); `min_degree` is its _MinDegreeStability argument (pass -1
+ *               for the reference's default) */
+int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double angle_step,
+                           double arc_step, double min_degree, int32_t* stable, double* degree,
+                           void* stream);
 
 /* ---- inputs ---------------------------------------------------------------------------- */
 

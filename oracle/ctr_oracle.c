@@ -536,3 +536,53 @@ int ctr_oracle_stability(const ctr_robot_desc* desc, const double* jv, double an
     scratch_free(&w);
     return stable;
 }
+
+/* ---- calcDegreeStability: robot_i.h:819-899 ----------------------------------------------- */
+int ctr_oracle_degree_stability(const ctr_robot_desc* desc, const double* jv, double angle_step,
+                                double arc_step, double min_degree, double* degree, int* stable_out)
+{
+    int rc = check_args(desc, jv, CTR_FK_MODE_STEP, arc_step, 1);
+    if (rc) return rc;
+    if (!(angle_step > 0.0) || !degree) return CTR_FK_E_ARG;
+    model_t m;
+    if ((rc = build_model(desc, &m))) return rc;
+    scratch_t w;
+    if ((rc = scratch_alloc(&w, m.maxs))) { scratch_free(&w); return rc; }
+    const int njv = 1 + m.S + m.T;
+    double q[CTR_FK_MAX_JV], prev[MAXT], cur[MAXT];
+    memcpy(q, jv, sizeof(double) * (size_t)njv);
+    q[0] = 0.0;                                                       /* :825 */
+    int stable = 1;
+    int checked = (min_degree > m.ztol) ? 0 : 1;                      /* :834 */
+    double smallest = 1.7976931348623157e308, result = 0.0;
+    int done = 0;
+    for (int s = 0; s < m.S && stable; ++s)
+        for (int k = 0; k < m.n[s] && stable; ++k) {
+            int t = m.t0[s] + k;
+            if (t == 0) continue;
+            int j = 2 + s + t;
+            double tipa = q[j], scan, scan_end;
+            if (tipa <= M_PI) { scan = 0.0; scan_end = tipa; }         /* :850-859 */
+            else              { scan = tipa; scan_end = 2.0 * M_PI; }
+            q[j] = scan;
+            if (base_angles(&m, &w, q, arc_step, prev)) { scratch_free(&w); return CTR_FK_E_ARG; }
+            scan += angle_step;
+            for (; scan <= scan_end; scan += angle_step) {            /* :870-891 */
+                q[j] = scan;
+                base_angles(&m, &w, q, arc_step, cur);
+                double rel = cur[t] - prev[t];
+                if (rel < smallest) {
+                    checked = 1;
+                    smallest = rel;
+                    if (rel < 0.0) { stable = 0; result = atan2(angle_step, rel); done = 1; break; }
+                }
+                memcpy(prev, cur, sizeof prev);
+            }
+            q[j] = jv[j];
+        }
+    if (!done) result = checked ? atan2(angle_step, smallest) : (min_degree + m.ztol);   /* :896-898 */
+    *degree = result;
+    if (stable_out) *stable_out = stable;
+    scratch_free(&w);
+    return 0;
+}

@@ -48,6 +48,10 @@ int ctr_oracle_jacobian(const ctr_robot_desc* desc, const double* jv, int32_t ns
 int ctr_oracle_stability(const ctr_robot_desc* desc, const double* jv, double angle_step,
                          double arc_step);
 
+/* calcDegreeStability, robot_i.h:819-899. */
+int ctr_oracle_degree_stability(const ctr_robot_desc* desc, const double* jv, double angle_step,
+                                double arc_step, double min_degree, double* degree, int* stable_out);
+
 int ctr_oracle_max_threads(void);
 
 #ifdef __cplusplus

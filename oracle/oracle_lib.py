@@ -31,6 +31,8 @@ def load():
         lib.ctr_oracle_jacobian.argtypes = [_P, _P, C.c_int32, C.c_double, C.c_double, _P, _P]
         lib.ctr_oracle_stability.restype = C.c_int
         lib.ctr_oracle_stability.argtypes = [_P, _P, C.c_double, C.c_double]
+        lib.ctr_oracle_degree_stability.restype = C.c_int
+        lib.ctr_oracle_degree_stability.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P]
         lib.ctr_oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -95,3 +97,13 @@ def jacobian(desc, jv, nsamples, fd_trans, fd_rot):
 def stability(desc, jv, angle_step, arc_step):
     jv = np.ascontiguousarray(jv, dtype=np.float64)
     return load().ctr_oracle_stability(C.addressof(desc), jv.ctypes.data, angle_step, arc_step)
+
+
+def degree_stability(desc, jv, angle_step, arc_step, min_degree=-1.0):
+    jv = np.ascontiguousarray(jv, dtype=np.float64)
+    deg = C.c_double(0.0); st = C.c_int(0)
+    rc = load().ctr_oracle_degree_stability(C.addressof(desc), jv.ctypes.data, angle_step, arc_step, min_degree,
+                                            C.addressof(deg), C.addressof(st))
+    if rc != 0:
+        raise RuntimeError("oracle degree_stability error %d" % rc)
+    return deg.value, st.value

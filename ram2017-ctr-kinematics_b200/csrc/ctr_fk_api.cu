@@ -385,6 +385,26 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
     return 0;
 }
 
+int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,
+                           double min_degree, int32_t* stable, double* degree, void* stream)
+{
+    int rc = check_common(h, jv, B, CTR_FK_MODE_STEP, arc_step, 0);
+    if (rc) return rc;
+    if (!(angle_step > 0.0) || !std::isfinite(angle_step) || !std::isfinite(min_degree)) {
+        set_error("angle step must be finite and > 0, min_degree finite");
+        return CTR_FK_E_ARG;
+    }
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    StabArgs a;
+    a.jv = jv; a.B = B; a.angle_step = angle_step; a.arc_step = arc_step; a.min_degree = min_degree;
+    a.stable = stable; a.degree = degree;
+    cudaError_t e = launch_stability(h->key, h->rb, a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail("stability kernel launch", e);
+    return 0;
+}
+
 int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B, double* jv, void* stream)
 {
     if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }

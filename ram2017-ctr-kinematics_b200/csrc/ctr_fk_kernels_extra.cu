@@ -111,5 +111,91 @@ cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStr
     return cudaGetLastError();
 }
 
-// FP32 variant: implemented in ctr_fk_kernels_f32.cu
+// ---- calcStability / calcDegreeStability (robot_i.h:756-899) -------------------------------------
+// One thread per configuration: for every tube 1..T-1 scan its tip angle and watch the tube's
+// base angle, which only needs the tip->base sweep (no frames).  The scan variable is advanced
+// and compared exactly like the reference (`scan += step; scan <= end`), because that decides
+// how many scan points exist.
+template <class L>
+__device__ __forceinline__ bool base_angles(const KRobot& rb, const double* q, double arc_step, double* alb)
+{
+    Ctl<L> c;
+    setup_control<L>(rb, q, 0, arc_step, 0, c);
+    if (c.status) return false;
+    solve_fast<L, false>(rb, c, nullptr, alb, NoSample{});
+    return true;
+}
+
+template <class L>
+__global__ void __launch_bounds__(kBlock)
+fk_stability_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ StabArgs a)
+{
+    constexpr int T = L::T, NJ = L::NJ;
+    const int64_t cfg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (cfg >= a.B) return;
+    double q[NJ];
+    load_jv<L>(a.jv, cfg, q);
+    q[0] = 0.0;                                                        // robot_i.h:762
+    const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * 3.14159265358979323846;
+    const double dstep = a.angle_step;
+    bool   stable = true, valid = true;
+    bool   checked = !(a.min_degree > rb.ztol);                        // :834
+    double smallest = 1.7976931348623157e308;                          // numeric_limits<Real>::max()
+    double prev[T], cur[T];
+
+#pragma unroll 1
+    for (int t = 1; t < T && stable && valid; ++t) {
+        const int jp = 2 + L::sec_of(t) + t;
+        double tipa = 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) tipa = (j == jp) ? q[j] : tipa;
+        double scan, scan_end;
+        if (tipa <= kPi) { scan = 0.0; scan_end = tipa; }              // :782-791
+        else             { scan = tipa; scan_end = kTwoPi; }
+        double qq[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) qq[j] = (j == jp) ? scan : q[j];
+        if (!base_angles<L>(rb, qq, a.arc_step, prev)) { valid = false; break; }
+        scan = x_add(scan, dstep);
+#pragma unroll 1
+        for (; scan <= scan_end; scan = x_add(scan, dstep)) {          // :802-813 / :870-891
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) qq[j] = (j == jp) ? scan : q[j];
+            base_angles<L>(rb, qq, a.arc_step, cur);
+            double rel = 0.0;
+#pragma unroll
+            for (int u = 0; u < T; ++u) rel = (u == t) ? cur[u] - prev[u] : rel;
+            if (rel < smallest) { checked = true; smallest = rel; }
+            if (rel < 0.0) { stable = false; break; }
+#pragma unroll
+            for (int u = 0; u < T; ++u) prev[u] = cur[u];
+        }
+    }
+    if (a.stable) a.stable[cfg] = valid ? (stable ? 1 : 0) : -1;
+    if (a.degree) {
+        double deg;
+        if (!valid) deg = __longlong_as_double(0x7ff8000000000000ll);
+        else if (checked) deg = atan2(dstep, smallest);                // :886, :897
+        else deg = a.min_degree + rb.ztol;                             // :898
+        a.degree[cfg] = deg;
+    }
+}
+
+cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, cudaStream_t st)
+{
+    if (a.B <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((a.B + kBlock - 1) / kBlock);
+    switch (key) {
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: \
+        fk_stability_kernel<Lay<S, A, Bq, C>><<<grid, kBlock, 0, st>>>(rb, a); \
+        break;
+        CTRK_FOR_EACH_LAYOUT_K(X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace ctrk

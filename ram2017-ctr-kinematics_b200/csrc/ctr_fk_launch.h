@@ -36,6 +36,14 @@ struct JacArgs {
     double*       tip;          // [B][12] nullable
 };
 
+struct StabArgs {
+    const double* jv;
+    int64_t       B;
+    double        angle_step, arc_step, min_degree;
+    int32_t*      stable;       // [B] nullable
+    double*       degree;       // [B] nullable
+};
+
 constexpr int kBlock = 128;     // threads per CTA for every solver kernel
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
@@ -47,6 +55,8 @@ cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cud
 cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 // finite-difference Jacobian (fast arithmetic)
 cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);
+// calcStability / calcDegreeStability scan (fast arithmetic, sweep only)
+cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, cudaStream_t st);
 
 // step-mode binning: sample count per configuration + histogram, then a counting sort that
 // yields `order` with the longest sweeps first (ctr_fk_kernels_util.cu)

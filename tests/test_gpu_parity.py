@@ -362,3 +362,30 @@ def test_f32_variant(ctrfk, oracle, robots, engines, name):
         dp, ang = util.pose_errors(o["tip"][ok], tip.cpu().numpy()[ok])
         assert dp.max() < TOL_F32_POS and ang.max() < TOL_F32_ROT, (dp.max(), ang.max())
         assert np.isnan(tip.cpu().numpy()[7]).all()
+
+
+@pytest.mark.parametrize("name", ["ctr_sec2_tub3.xml", "ctr_sec3_tub5.xml"])
+def test_stability_parity(ctrfk, oracle, robots, engines, name):
+    """calcStability / calcDegreeStability: the flag must match exactly; the degree is an atan2 of
+    a difference of base angles (1e-13-level arithmetic differences), compared to 1e-7."""
+    d = robots[name]
+    B = 600
+    jv_np = ctrfk.sample_joints_host(d, 31, 0, B)
+    jv_np[5, 1] = -0.5                                      # invalid -> -1 / NaN
+    jv = torch.from_numpy(jv_np).cuda()
+    stable = torch.full((B,), 9, dtype=torch.int32, device="cuda")
+    degree = torch.zeros(B, dtype=torch.float64, device="cuda")
+    astep, step = 0.1, d.max_length / 256.0
+    engines[name].stability(jv, B, astep, step, -1.0, stable, degree, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st, dg = stable.cpu().numpy(), degree.cpu().numpy()
+    assert st[5] == -1 and np.isnan(dg[5])
+    n_unstable = 0
+    for i in range(B):
+        if i == 5:
+            continue
+        want_deg, want_st = oracle.degree_stability(d, jv_np[i], astep, step, -1.0)
+        assert st[i] == want_st == oracle.stability(d, jv_np[i], astep, step), i
+        assert abs(dg[i] - want_deg) < 1e-7, (i, dg[i], want_deg)
+        n_unstable += (want_st == 0)
+    assert 0 < n_unstable < B

@@ -221,7 +221,19 @@ def test_jacobian_structure(ctrfk, oracle, robots):
         assert np.abs((tp - tip[9:]) / 1e-6 - J[j, :3]).max() < 1e-9
 
 
-def test_stability_runs(ctrfk, oracle, robots):
+def test_stability_and_degree(ctrfk, oracle, robots):
+    """calcStability / calcDegreeStability (robot_i.h:756-899): short, barely curved overlaps are
+    stable; long overlaps of strongly precurved tubes lose monotonicity of the base angle."""
     d = robots["ctr_sec2_tub3.xml"]
-    q = np.array([0.0, 0.02, 0.0, 0.5, 0.02, 0.7])
-    assert oracle.stability(d, q, 0.05, d.max_length / 256.0) in (0, 1)
+    step = d.max_length / 256.0
+    q_short = np.array([0.0, 0.005, 0.0, 0.5, 0.005, 0.7])
+    assert oracle.stability(d, q_short, 0.05, step) == 1
+    deg, st = oracle.degree_stability(d, q_short, 0.05, step)
+    assert st == 1 and 0.0 < deg < np.pi / 2
+    jv = ctrfk.sample_joints_host(d, 4, 0, 300)
+    flags = np.array([oracle.stability(d, q, 0.1, step) for q in jv])
+    degs = np.array([oracle.degree_stability(d, q, 0.1, step) for q in jv])
+    assert np.array_equal(flags, degs[:, 1].astype(int))
+    assert 0 < flags.sum() < len(flags)                      # both outcomes occur
+    assert (degs[flags == 0, 0] > np.pi / 2).all()           # atan2(step, negative) > pi/2
+    assert (degs[flags == 1, 0] <= np.pi / 2).all()
