@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1_000_000, help="configurations per GPU per step")
     ap.add_argument("--mode", default="F", choices=["F", "S"], help="F: fixed N samples; S: arc-length step")
     ap.add_argument("--nsamples", type=int, default=256)
+    ap.add_argument("--max-samples", type=int, default=256, help="MaxSamples of the robot (install.sh:96 uses 256)")
     ap.add_argument("--strict", action="store_true", help="STRICT arithmetic kernels")
     ap.add_argument("--backbone", action="store_true", help="full backbone + radius output (config 4)")
     ap.add_argument("--f32", action="store_true", help="FP32 state arithmetic variant")
@@ -153,7 +154,7 @@ def run_reference(a):
         return 0
     import ctrfk
     import oracle_lib
-    desc = ctrfk.desc_from_xml(ctrfk.resource(a.robot), 256)
+    desc = ctrfk.desc_from_xml(ctrfk.resource(a.robot), a.max_samples)
     threads = host_threads()
     seed = 20171
     # bounded sample per step: ~1 s of CPU work, so K+W steps end within minutes
@@ -201,7 +202,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
 
-    desc = ctrfk.desc_from_xml(ctrfk.resource(a.robot), 256)
+    desc = ctrfk.desc_from_xml(ctrfk.resource(a.robot), a.max_samples)
     eng = ctrfk.Engine(desc, local)
     B, njv = a.batch, desc.njoints
     seed = {"ctr_sec2_tub3.xml": 20171, "ctr_sec3_tub3.xml": 20172, "ctr_sec3_tub4.xml": 20173,
@@ -222,8 +223,8 @@ def main():
         tips.append(torch.empty(B, 12, dtype=torch.float64, device="cuda"))
     if a.backbone:
         for s in range(NSET):
-            bbs.append(torch.empty(B, 256, 12, dtype=torch.float64, device="cuda"))
-            rds.append(torch.empty(B, 256, dtype=torch.float64, device="cuda"))
+            bbs.append(torch.empty(B, a.max_samples, 12, dtype=torch.float64, device="cuda"))
+            rds.append(torch.empty(B, a.max_samples, dtype=torch.float64, device="cuda"))
     gathered = torch.empty(world * B, 12, dtype=torch.float64, device="cuda") if (a.allgather and world > 1) else None
 
     def one_step(i):
