@@ -183,6 +183,27 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
                            double arc_step, double min_degree, int32_t* stable, double* degree,
                            void* stream);
 
+/* Base-angle-actuated forward kinematics (not in the reference): the alpha
+ * slots of `jv_base` hold the tube angles AT THE BASE (what the actuators set) instead of at the
+ * tip.  A Newton shooting solve finds the tip angles whose reference sweep ends at those base
+ * angles (Jacobian from the tangent-linear sweep), then the ordinary solve produces the pose.
+ * Iteration counts differ per configuration; the kernel is persistent and every lane draws its
+ * next configuration from a global ticket counter as soon as it converges.
+ *   jv_tip [B][n_jv]  out, REQUIRED: jv_base with the alpha slots replaced by the tip angles found
+ *                     (feeding it to ctr_fk_batch reproduces `tip`); tube 0's angle passes through
+ *   tip    [B][12]    out, nullable
+ *   iters  [B]        out, nullable: Newton updates applied
+ *   status [B]        out, nullable: 0 converged (max |base - wanted| <= tol), 1 Phi out of range,
+ *                     2 singular Jacobian (bifurcation point), 3 max_iter reached
+ * DEVICE pointers. */
+#define CTR_FK_SHOOT_OK        0
+#define CTR_FK_SHOOT_PHI_RANGE 1
+#define CTR_FK_SHOOT_SINGULAR  2
+#define CTR_FK_SHOOT_MAX_ITER  3
+int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mode, double step,
+                      int32_t nsamples, double tol, int32_t max_iter, double* jv_tip, double* tip,
+                      int32_t* iters, int32_t* status, void* stream);
+
 /* ---- inputs ---------------------------------------------------------------------------- */
 
 /* Fill jv[B][n_jv] (DEVICE pointer) with the distribution of getRandomJointValues

@@ -405,6 +405,38 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
     return 0;
 }
 
+int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mode, double step, int32_t nsamples,
+                      double tol, int32_t max_iter, double* jv_tip, double* tip, int32_t* iters, int32_t* status,
+                      void* stream)
+{
+    int rc = check_common(h, jv_base, B, mode, step, nsamples);
+    if (rc) return rc;
+    if (B > 0 && !jv_tip) { set_error("jv_tip output is required"); return CTR_FK_E_NULL; }
+    if (!(tol > 0.0) || !std::isfinite(tol) || max_iter < 1) { set_error("tol must be > 0 and max_iter >= 1"); return CTR_FK_E_ARG; }
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* ticket = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&ticket, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail("ticket allocation", e);
+    e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
+    int32_t* order = nullptr;
+    if (e == cudaSuccess && mode == CTR_FK_MODE_STEP && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples)
+        e = make_order(h, jv_base, B, mode, step, nsamples, &order, st);   // longest sweeps first
+    if (e == cudaSuccess) {
+        ShootArgs a;
+        a.jv_base = jv_base; a.B = B; a.mode = mode; a.step = step; a.nsamples = nsamples; a.tol = tol;
+        a.max_iter = max_iter; a.order = order; a.jv_tip = jv_tip; a.iters = iters; a.status = status; a.ticket = ticket;
+        e = launch_shoot(h->key, h->rb, a, h->sm_count, st);
+    }
+    if (order) cudaFreeAsync(order, st);
+    cudaFreeAsync(ticket, st);
+    if (e != cudaSuccess) return cuda_fail("shooting kernel launch", e);
+    if (tip) return run_batch(h, jv_tip, B, mode, step, nsamples, 0u, tip, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+    return 0;
+}
+
 int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B, double* jv, void* stream)
 {
     if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }

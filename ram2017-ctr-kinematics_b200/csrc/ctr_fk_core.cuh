@@ -916,6 +916,192 @@ CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* a
 }
 
 
+// ---- tangent-linear sweep: base angles and their Jacobian w.r.t. the tip angles -----------------
+// The reference's operator maps tip angles to base angles (m_SampleTubeAlpha after the sweep,
+// robot_i.h:810 reads it as such).  A robot actuated at the base needs the inverse: find the tip
+// angles whose sweep ends at given base angles (the "shooting solve" of the
+// north star).  This routine runs the same discrete sweep as solve_fast and carries, next to the
+// state (alpha_t, z_t), its exact derivative with respect to the tip angles of tubes 1..T-1 (the
+// variational equations of the discrete recurrence), so Newton's method on the base-angle
+// residual converges quadratically to a root of the *reference's own* discretisation.
+//   base[t]      = alpha_t at the base, t = 0..T-1
+//   jac[r*(T-1)+c] = d base[r+1] / d alpha_tip[c+1]
+template <class L>
+CTR_HD void sweep_tangent(const KRobot& rb, const Ctl<L>& c, double* base, double* jac)
+{
+    constexpr int S = L::S, T = L::T, U = (T > 1 ? T - 1 : 1);
+    double al[T], uz[T], dal[T][U], duz[T][U];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        al[t] = c.al[t]; uz[t] = 0.0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) { dal[t][j] = (t == j + 1) ? 1.0 : 0.0; duz[t][j] = 0.0; }
+    }
+    double hko[U];
+#pragma unroll
+    for (int t = 0; t + 1 < T; ++t) hko[t] = c.h * rb.onu[t] * rb.kappa[L::sec_of(t)];
+    double pos = c.arc_end;
+#pragma unroll 1
+    for (int k = c.n - 1; k >= 1; --k) {          // the last sample (k = 0) does not update the state
+        double sn[T], cs[T];
+        if (k == c.n - 1) fast_sincos(al[0], sn[0], cs[0]);
+        else { sn[0] = 0.0; cs[0] = 1.0; }
+#pragma unroll
+        for (int t = 1; t < T; ++t) fast_sincos(al[t], sn[t], cs[t]);
+        bool in_k[S], in_c[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            in_k[s] = (s == S - 1) ? true : le_nonneg(pos, c.end[s]);
+            in_c[s] = in_k[s] && le_nonneg(c.start[s], pos);
+        }
+        double rks = rb.rk[S - 1];
+#pragma unroll
+        for (int s = S - 2; s >= 0; --s) rks = in_k[s] ? rb.rk[s] : rks;
+        double cx = 0.0, cy = 0.0, dcx[U], dcy[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { dcx[j] = 0.0; dcy[j] = 0.0; }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double g = in_c[s] ? rb.kg[s] : 0.0;
+#pragma unroll
+            for (int jt = 0; jt < L::nt(s); ++jt) {
+                const int t = L::t0(s) + jt;
+                cx = x_fma(-sn[t], g, cx);
+                cy = x_fma(cs[t], g, cy);
+                if (t >= 1) {
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        dcx[j] = x_fma(-cs[t] * g, dal[t][j], dcx[j]);
+                        dcy[j] = x_fma(-sn[t] * g, dal[t][j], dcy[j]);
+                    }
+                }
+            }
+        }
+        cx *= rks; cy *= rks;
+#pragma unroll
+        for (int j = 0; j < U; ++j) { dcx[j] *= rks; dcy[j] *= rks; }
+        double ux[T], dux[T][U];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            ux[t] = x_fma(cs[t], cx, sn[t] * cy);
+            const double uy = x_fma(cs[t], cy, -(sn[t] * cx));      // d ux / d alpha_t
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                dux[t][j] = x_fma(uy, (t >= 1 ? dal[t][j] : 0.0), x_fma(cs[t], dcx[j], sn[t] * dcy[j]));
+        }
+        // angles with the previous sample's torsion
+        const double z0 = uz[0];
+        al[0] = 0.0;
+#pragma unroll
+        for (int t = 1; t < T; ++t) {
+            al[t] = x_fma(c.h, uz[t] - z0, al[t]);
+#pragma unroll
+            for (int j = 0; j < U; ++j) dal[t][j] = x_fma(c.h, duz[t][j] - duz[0][j], dal[t][j]);
+        }
+        // torsion
+        if (T > 1) {
+            double cz = 0.0, dcz[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) dcz[j] = 0.0;
+#pragma unroll
+            for (int t = T - 2; t >= 0; --t) {
+                const double hk = in_c[L::sec_of(t)] ? hko[t] : 0.0;
+                cz = x_fma(rb.czc[t], uz[t], cz);
+                uz[t] = x_fma(hk, ux[t], uz[t]);
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    dcz[j]    = x_fma(rb.czc[t], duz[t][j], dcz[j]);
+                    duz[t][j] = x_fma(hk, dux[t][j], duz[t][j]);
+                }
+            }
+            uz[T - 1] = -cz * rb.cl;
+#pragma unroll
+            for (int j = 0; j < U; ++j) duz[T - 1][j] = -dcz[j] * rb.cl;
+        }
+        pos = x_sub(pos, c.h);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) base[t] = al[t];
+    if (jac) {
+#pragma unroll
+        for (int r = 0; r + 1 < T; ++r)
+#pragma unroll
+            for (int j = 0; j + 1 < T; ++j) jac[r * (T - 1) + j] = dal[r + 1][j];
+    }
+}
+
+// Solve the U x U system  J d = f  in place (Gaussian elimination with partial pivoting; U <= 5).
+// Returns false when a pivot vanishes (singular Jacobian: a bifurcation point of the robot).
+template <int U>
+CTR_HD bool solve_small(double* J, double* f)
+{
+#pragma unroll
+    for (int col = 0; col < U; ++col) {
+        int piv = col;
+        double best = fabs(J[col * U + col]);
+#pragma unroll
+        for (int r = col + 1; r < U; ++r) {
+            const double v = fabs(J[r * U + col]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (!(best > 1e-300)) return false;
+#pragma unroll
+        for (int r = col + 1; r < U; ++r) {
+            if (r == piv) {
+#pragma unroll
+                for (int cc = 0; cc < U; ++cc) { const double tmp = J[col * U + cc]; J[col * U + cc] = J[r * U + cc]; J[r * U + cc] = tmp; }
+                const double tf = f[col]; f[col] = f[r]; f[r] = tf;
+            }
+        }
+        const double inv = 1.0 / J[col * U + col];
+#pragma unroll
+        for (int r = col + 1; r < U; ++r) {
+            const double m = J[r * U + col] * inv;
+#pragma unroll
+            for (int cc = col; cc < U; ++cc) J[r * U + cc] = x_fma(-m, J[col * U + cc], J[r * U + cc]);
+            f[r] = x_fma(-m, f[col], f[r]);
+        }
+    }
+#pragma unroll
+    for (int r = U - 1; r >= 0; --r) {
+        double acc = f[r];
+#pragma unroll
+        for (int cc = r + 1; cc < U; ++cc) acc = x_fma(-J[r * U + cc], f[cc], acc);
+        f[r] = acc / J[r * U + r];
+    }
+    return true;
+}
+
+// One Newton iteration of the base-angle shooting problem.  q holds the joint vector with the
+// CURRENT tip-angle estimate; beta[t] the wanted base angles (t >= 1).  Returns the residual
+// max-norm BEFORE the update; q's tip angles are updated in place unless converged.
+// status: 0 running / converged decided by the caller, 2 = singular Jacobian, 1 = phi out of range
+template <class L>
+CTR_HD double shoot_iteration(const KRobot& rb, double* q, const double* beta, int mode, double step,
+                              int nsamples, double tol, int& status)
+{
+    constexpr int T = L::T, U = (T > 1 ? T - 1 : 1);
+    Ctl<L> c;
+    setup_control<L>(rb, q, mode, step, nsamples, c);
+    if (c.status) { status = 1; return 0.0; }
+    double base[T], J[U * U], f[U];
+    sweep_tangent<L>(rb, c, base, T > 1 ? J : nullptr);
+    double res = 0.0;
+#pragma unroll
+    for (int r = 0; r + 1 < T; ++r) { f[r] = base[r + 1] - beta[r + 1]; res = fmax(res, fabs(f[r])); }
+    if (T == 1 || res <= tol) return res;
+    if (!solve_small<U>(J, f)) { status = 2; return res; }
+    // step limiter: tube angles are periodic, a Newton step larger than 1 rad is an overshoot
+#pragma unroll
+    for (int r = 0; r + 1 < T; ++r) {
+        const double d = fmin(1.0, fmax(-1.0, f[r]));
+        const int t = r + 1;
+        const int j = 2 + L::sec_of(t) + t;
+        q[j] = q[j] - d;
+    }
+    return res;
+}
+
 // ---- rigid transform as (unit quaternion, translation): used by the warp-parallel backbone pass
 struct QT {
     double w, x, y, z, px, py, pz;

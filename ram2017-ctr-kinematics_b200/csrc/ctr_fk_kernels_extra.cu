@@ -198,4 +198,91 @@ cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, cudaS
     return cudaGetLastError();
 }
 
+// ---- base-angle shooting solve ----------------------------------------------
+// Newton iterations per configuration vary (mean ~5, tail beyond 50 near bifurcations).  The
+// kernel is persistent: grid = resident CTAs of the device; every lane owns one configuration at a
+// time and, when it converges, draws the next index from a global ticket counter (one atomicAdd
+// per warp and refill round, ranks by ballot).  All lanes of a warp execute one Newton iteration
+// (one tangent-linear sweep, uniform trip count in fixed-N mode) per round, so nobody waits for a
+// slow neighbour to finish all of its iterations.
+template <class L>
+__global__ void __launch_bounds__(kBlock)
+fk_shoot_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ ShootArgs a)
+{
+    constexpr int T = L::T, NJ = L::NJ;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int64_t cfg = -1;
+    int     it = 0;
+    double  q[NJ], beta[T];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q[j] = 0.0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) beta[t] = 0.0;
+    bool drained = false;                                   // queue exhausted (warp-uniform)
+    for (;;) {
+        // ---- refill idle lanes from the ticket queue ---------------------------------------------
+        const bool need = (cfg < 0) && !drained;
+        const unsigned m = __ballot_sync(full, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long first = 0;
+            if (lane == leader) first = atomicAdd(a.ticket, (unsigned long long)__popc(m));
+            first = __shfl_sync(full, first, leader);
+            if (need) {
+                const int64_t idx = (int64_t)first + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.B) {
+                    cfg = a.order ? (int64_t)a.order[idx] : idx;
+                    load_jv<L>(a.jv_base, cfg, q);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) beta[t] = q[2 + L::sec_of(t) + t];
+                    it = 0;
+                }
+            }
+            if ((int64_t)first + __popc(m) >= a.B) drained = true;
+        }
+        if (__ballot_sync(full, cfg >= 0) == 0) break;       // nothing left for this warp
+        // ---- one Newton iteration on every busy lane ---------------------------------------------
+        if (cfg >= 0) {
+            int st = 0;
+            const double res = shoot_iteration<L>(rb, q, beta, a.mode, a.step, a.nsamples, a.tol, st);
+            bool done = false;
+            if (st) done = true;
+            else if (res <= a.tol) done = true;
+            else if (it + 1 >= a.max_iter) { st = 3; ++it; done = true; }
+            else ++it;
+            if (done) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a.jv_tip[cfg * NJ + j] = q[j];
+                if (a.iters) a.iters[cfg] = it;
+                if (a.status) a.status[cfg] = st;
+                cfg = -1;
+            }
+        }
+    }
+}
+
+cudaError_t launch_shoot(int key, const KRobot& rb, const ShootArgs& a, int sm_count, cudaStream_t st)
+{
+    if (a.B <= 0) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    switch (key) {
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: { \
+        int per_sm = 0; \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_shoot_kernel<Lay<S, A, Bq, C>>, kBlock, 0); \
+        if (e != cudaSuccess) return e; \
+        if (per_sm < 1) per_sm = 1; \
+        int64_t want = (a.B + kBlock - 1) / kBlock; \
+        int64_t cap = (int64_t)per_sm * sm_count; \
+        fk_shoot_kernel<Lay<S, A, Bq, C>><<<(unsigned)(want < cap ? want : cap), kBlock, 0, st>>>(rb, a); \
+        break; }
+        CTRK_FOR_EACH_LAYOUT_K(X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace ctrk

@@ -44,6 +44,21 @@ struct StabArgs {
     double*       degree;       // [B] nullable
 };
 
+struct ShootArgs {
+    const double*       jv_base;
+    int64_t             B;
+    int                 mode;
+    double              step;
+    int                 nsamples;
+    double              tol;
+    int                 max_iter;
+    const int32_t*      order;      // nullable
+    double*             jv_tip;     // [B][NJ]
+    int32_t*            iters;      // nullable
+    int32_t*            status;     // nullable
+    unsigned long long* ticket;     // zero-initialised work counter
+};
+
 constexpr int kBlock = 128;     // threads per CTA for every solver kernel
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
@@ -57,6 +72,8 @@ cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, c
 cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);
 // calcStability / calcDegreeStability scan (fast arithmetic, sweep only)
 cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, cudaStream_t st);
+// base-angle shooting solve: persistent kernel with a ticket queue (grid sized to the device)
+cudaError_t launch_shoot(int key, const KRobot& rb, const ShootArgs& a, int sm_count, cudaStream_t st);
 
 // step-mode binning: sample count per configuration + histogram, then a counting sort that
 // yields `order` with the longest sweeps first (ctr_fk_kernels_util.cu)

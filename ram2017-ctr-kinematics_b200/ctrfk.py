@@ -17,6 +17,7 @@ MODE_STEP, MODE_NSAMPLE = 0, 1
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
+SHOOT_OK, SHOOT_PHI_RANGE, SHOOT_SINGULAR, SHOOT_MAX_ITER = 0, 1, 2, 3
 
 
 class SectionDesc(C.Structure):
@@ -69,6 +70,8 @@ SYMBOLS = {
     "ctr_fk_jacobian_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P, _P]),
     "ctr_fk_jacobian_host": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P]),
     "ctr_fk_stability_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
+    "ctr_fk_batch_base": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_double, C.c_int32,
+                                    _P, _P, _P, _P, _P]),
     "ctr_fk_sample_joints": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
     "ctr_fk_sample_joints_host": (C.c_int, [C.POINTER(RobotDesc), C.c_uint64, C.c_int64, C.c_int64, _P]),
     "ctr_fk_count_samples_host": (C.c_int, [C.POINTER(RobotDesc), _P, C.c_int64, C.c_int, C.c_double,
@@ -200,6 +203,11 @@ class Engine:
     def stability(self, jv, B, angle_step, arc_step, min_degree=-1.0, stable=None, degree=None, stream=None):
         _check(load().ctr_fk_stability_batch(self.handle, _ptr(jv), B, angle_step, arc_step, min_degree,
                                              _ptr(stable), _ptr(degree), stream))
+
+    def batch_base(self, jv_base, B, mode, step=0.0, nsamples=0, tol=1e-11, max_iter=60, jv_tip=None, tip=None,
+                   iters=None, status=None, stream=None):
+        _check(load().ctr_fk_batch_base(self.handle, _ptr(jv_base), B, mode, step, nsamples, tol, max_iter,
+                                        _ptr(jv_tip), _ptr(tip), _ptr(iters), _ptr(status), stream))
 
     def sample_joints(self, seed, first, B, jv, stream=None):
         _check(load().ctr_fk_sample_joints(self.handle, seed, first, B, _ptr(jv), stream))

@@ -71,3 +71,42 @@ extern "C" void hostsim_se3(double ux, double uy, double uz, double h, double* s
     tf_step_strict(ux, uy, uz, h, 1e-12, strict12);
     se3_step_fast(ux, uy, uz, h, 1e-12, fast7[0], fast7[1], fast7[2], fast7[3], fast7[4], fast7[5], fast7[6]);
 }
+
+// Base-angle shooting on the CPU build of the device code: jv_base holds base angles in the alpha
+// slots; returns tip-angle joint vectors in jv_tip, iteration counts and status.
+namespace {
+template <class L>
+void shoot_run(const KRobot& rb, const double* jvb, int64_t B, int mode, double step, int ns, double tol, int maxit,
+               double* jv_tip, int32_t* iters, int32_t* status)
+{
+    for (int64_t i = 0; i < B; ++i) {
+        double q[L::NJ], beta[L::T];
+        for (int j = 0; j < L::NJ; ++j) q[j] = jvb[i * L::NJ + j];
+        for (int t = 0; t < L::T; ++t) beta[t] = q[2 + L::sec_of(t) + t];
+        int st = 0, it = 0;
+        for (;; ++it) {
+            double res = shoot_iteration<L>(rb, q, beta, mode, step, ns, tol, st);
+            if (st) break;
+            if (res <= tol) break;
+            if (it + 1 >= maxit) { st = 3; ++it; break; }
+        }
+        for (int j = 0; j < L::NJ; ++j) jv_tip[i * L::NJ + j] = q[j];
+        iters[i] = it; status[i] = st;
+    }
+}
+}  // namespace
+
+extern "C" int hostsim_shoot(const ctr_robot_desc* d, const double* jvb, int64_t B, int mode, double step, int ns,
+                             double tol, int maxit, double* jv_tip, int32_t* iters, int32_t* status)
+{
+    KRobot rb;
+    int rc = make_krobot(d, &rb);
+    if (rc) return rc;
+    switch (layout_key(d)) {
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: shoot_run<Lay<S, A, Bq, C>>(rb, jvb, B, mode, step, ns, tol, maxit, jv_tip, iters, status); break;
+        CTRK_FOR_EACH_LAYOUT(X)
+#undef X
+        default: return CTR_FK_E_DESC;
+    }
+    return 0;
+}

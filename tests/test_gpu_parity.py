@@ -392,3 +392,40 @@ def test_stability_parity(ctrfk, oracle, robots, engines, name):
         assert abs(dg[i] - want_deg) < 1e-7, (i, dg[i], want_deg)
         n_unstable += (want_st == 0)
     assert 0 < n_unstable < B
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+@pytest.mark.parametrize("mode", [1, 0], ids=["fixedN", "step"])
+def test_base_angle_shooting(ctrfk, oracle, robots, engines, name, mode):
+    """ctr_fk_batch_base: persistent Newton shooting kernel.  Checker = the reference sweep (oracle)
+    at the tip angles found; the pose must equal the oracle's pose at those tip angles."""
+    d = robots[name]
+    eng = engines[name]
+    B = 30_000
+    kw = dict(nsamples=128) if mode == 1 else dict(step=d.max_length / 128.0)
+    jv = ctrfk.sample_joints_host(d, 78, 0, B)
+    o = oracle.fk_batch(d, jv, mode, **kw)
+    jvb_np = util.base_angle_inputs(d, jv, o["alpha_base"])
+    jvb_np[11, 1] = -1.0                                    # invalid Phi
+    jvb = torch.from_numpy(jvb_np).cuda()
+    jt = torch.full((B, d.njoints), -9.0, dtype=torch.float64, device="cuda")
+    tip = torch.zeros(B, 12, dtype=torch.float64, device="cuda")
+    it = torch.full((B,), -9, dtype=torch.int32, device="cuda")
+    st = torch.full((B,), -9, dtype=torch.int32, device="cuda")
+    before = ctrfk.launch_count()
+    eng.batch_base(jvb, B, mode, tol=1e-11, max_iter=60, jv_tip=jt, tip=tip, iters=it, status=st,
+                   stream=torch.cuda.current_stream().cuda_stream, **kw)
+    torch.cuda.synchronize()
+    assert ctrfk.launch_count() >= before + 2
+    jt_np, tip_np, it_np, st_np = jt.cpu().numpy(), tip.cpu().numpy(), it.cpu().numpy(), st.cpu().numpy()
+    assert (st_np >= 0).all() and (it_np >= 0).all() and (jt_np != -9.0).all()     # every ticket was served once
+    assert st_np[11] == ctrfk.SHOOT_PHI_RANGE and np.isnan(tip_np[11]).all()
+    ok = st_np == 0
+    assert ok.mean() > 0.85
+    o2 = oracle.fk_batch(d, jt_np, mode, **kw)
+    good = ok & (o2["status"] == 0)
+    res = np.abs(o2["alpha_base"][good][:, 1:] - jvb_np[good][:, util.alpha_indices(d)[1:]]).max(axis=1)
+    assert res.max() < 1e-9                                 # roots confirmed by the reference sweep
+    dp, ang = util.pose_errors(o2["tip"][good], tip_np[good])
+    assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+    assert it_np[ok].max() >= it_np[ok].min() + 5           # divergent iteration counts were absorbed

@@ -121,3 +121,31 @@ def test_f32_solver_logic(ctrfk, oracle, hostsim, robots, name):
         assert np.array_equal(o["n"], s["n"]) and np.array_equal(o["step"], s["step"])
         dp, ang = util.pose_errors(o["tip"], s["tip"])
         assert dp.max() < TOL_F32_POS and ang.max() < TOL_F32_ROT, (dp.max(), ang.max())
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_shooting_solve_logic(ctrfk, oracle, hostsim, robots, name):
+    """Base-angle shooting, CPU build of the device code.  Its checker is the
+    reference sweep itself: the oracle, run at the tip angles found, must end at the wanted base
+    angles.  Inputs are base angles produced by the oracle from random tip angles, so a root
+    exists; robots this curved have several roots for many inputs, so the root found need not be
+    the one the input came from."""
+    import ctypes as C
+    d = robots[name]
+    B = 400
+    jv = ctrfk.sample_joints_host(d, 77, 0, B)
+    o = oracle.fk_batch(d, jv, ctrfk.MODE_NSAMPLE, nsamples=128)
+    jvb = util.base_angle_inputs(d, jv, o["alpha_base"])
+    jt = np.zeros_like(jv); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+    rc = hostsim.hostsim_shoot(C.addressof(d), jvb.ctypes.data, B, ctrfk.MODE_NSAMPLE, 0.0, 128, 1e-11, 60,
+                               jt.ctypes.data, it.ctypes.data, st.ctypes.data)
+    assert rc == 0
+    ok = st == 0
+    assert ok.mean() > 0.85 and set(np.unique(st)) <= {0, 2, 3}
+    o2 = oracle.fk_batch(d, jt, ctrfk.MODE_NSAMPLE, nsamples=128)
+    res = np.abs(o2["alpha_base"][:, 1:] - o["alpha_base"][:, 1:]).max(axis=1)
+    assert res[ok].max() < 1e-10                       # the reference sweep confirms every root
+    assert it[ok].max() > it[ok].min() + 5             # iteration counts really diverge
+    idx = util.alpha_indices(d)
+    assert np.array_equal(jt[:, [i for i in range(jv.shape[1]) if i not in idx[1:]]],
+                          jv[:, [i for i in range(jv.shape[1]) if i not in idx[1:]]])   # only alphas 1.. change

@@ -32,6 +32,9 @@ def load_hostsim():
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hostsim_sincos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.hostsim_se3.argtypes = [C.c_double] * 4 + [C.c_void_p] * 2
+    lib.hostsim_shoot.restype = C.c_int
+    lib.hostsim_shoot.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -84,3 +87,22 @@ def edge_joint_sets(desc):
                 q[i] = a if a is not None else rng.uniform(0, two_pi_m)
             rows.append(q)
     return np.array(rows)
+
+
+def alpha_indices(desc):
+    """Joint-vector index of every tube's angle."""
+    idx, t0 = [], 0
+    for s in range(desc.nsections):
+        for k in range(desc.sec[s].ntube):
+            idx.append(2 + s + t0 + k)
+        t0 += desc.sec[s].ntube
+    return idx
+
+
+def base_angle_inputs(desc, jv_tip, alpha_base):
+    """Joint vectors whose alpha slots carry the BASE angles of the given sweep results."""
+    jvb = np.array(jv_tip, copy=True)
+    idx = alpha_indices(desc)
+    for t in range(1, len(idx)):
+        jvb[:, idx[t]] = alpha_base[:, t]
+    return jvb
