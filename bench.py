@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--strict", action="store_true", help="STRICT arithmetic kernels")
     ap.add_argument("--backbone", action="store_true", help="full backbone + radius output (config 4)")
     ap.add_argument("--f32", action="store_true", help="FP32 state arithmetic variant")
+    ap.add_argument("--shoot", action="store_true", help="base-angle shooting solve (ctr_fk_batch_base) instead of FK")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="configurations of the CPU baseline sample (0 = auto)")
@@ -227,9 +228,27 @@ def main():
             rds.append(torch.empty(B, a.max_samples, dtype=torch.float64, device="cuda"))
     gathered = torch.empty(world * B, 12, dtype=torch.float64, device="cuda") if (a.allgather and world > 1) else None
 
+    shoot = None
+    if a.shoot:
+        # inputs: base angles reached from the random tip angles (so a root exists for every input)
+        import util
+        idx = util.alpha_indices(desc)
+        shoot = []
+        for s in range(NSET):
+            ab = torch.empty(B, desc.ntubes, dtype=torch.float64, device="cuda")
+            eng.batch(jvs[s], B, mode, step=step_len, nsamples=a.nsamples, alpha_base=ab, stream=stream)
+            jb = jvs[s].clone()
+            for t in range(1, desc.ntubes):
+                jb[:, idx[t]] = ab[:, t]
+            shoot.append(dict(jvb=jb, jt=torch.empty_like(jb), it=torch.empty(B, dtype=torch.int32, device="cuda"),
+                              st=torch.empty(B, dtype=torch.int32, device="cuda")))
+
     def one_step(i):
         s = i % NSET
-        if a.f32:
+        if a.shoot:
+            eng.batch_base(shoot[s]["jvb"], B, mode, step=step_len, nsamples=a.nsamples, tol=1e-11, max_iter=60,
+                           jv_tip=shoot[s]["jt"], tip=tips[s], iters=shoot[s]["it"], status=shoot[s]["st"], stream=stream)
+        elif a.f32:
             eng.batch_f32(jvs[s], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[s], stream=stream)
         else:
             eng.batch(jvs[s], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[s],
@@ -291,7 +310,9 @@ def main():
     prof_json = os.path.join(REPO, "profiles", "dram_traffic.json")
     if os.path.exists(prof_json):
         try:
-            traffic = json.load(open(prof_json)).get(("backbone" if a.backbone else "tip") + "_" + a.mode)
+            ent = json.load(open(prof_json)).get(("backbone" if a.backbone else "tip") + "_" + a.mode)
+            if ent and ent["robot"] == a.robot and ent["batch"] == B and not (a.strict or a.f32 or a.shoot):
+                traffic = ent["bytes"]
         except Exception:
             traffic = None
     if a.backbone:
@@ -340,7 +361,7 @@ def main():
             best = max(best, src.numel() * 8 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
         pcie[name] = best
     e2e = None
-    if not a.backbone and not a.f32:
+    if not a.backbone and not a.f32 and not a.shoot:
         e2e_steps = max(3, min(a.steps, 10))
         for _ in range(2):
             eng.batch_host(h_jv, B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=h_tip)
@@ -363,7 +384,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample ---------------------------
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.shoot:
         threads = host_threads()
         r1, _ = cpu_reference_rate(desc, a, 1, 2048, seed)
         sample = a.cpu_sample or int(min(B, max(20000, r1 * threads * 10.0)))      # ~10 s of CPU work
@@ -381,6 +402,11 @@ def main():
                            "l2": "two alternating input/output sets of %.0f MB each (> 126 MB L2 together and singly)" % ((njv * 8 + 96) * B / 1e6),
                            "collective": "all_gather(tip)" if gathered is not None else "none"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches}
+        if a.shoot:
+            it = shoot[0]["it"].cpu().numpy(); stt = shoot[0]["st"].cpu().numpy()
+            line["shoot"] = {"converged_frac": float((stt == 0).mean()), "mean_iters": float(it[stt == 0].mean()),
+                             "max_iters": int(it.max()), "sweeps_per_config": float(it.mean() + 1)}
+            line["config"]["workload"] += " [base-angle shooting solve, not the headline FK]"
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

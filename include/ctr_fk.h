@@ -182,6 +182,9 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
 int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double angle_step,
                            double arc_step, double min_degree, int32_t* stable, double* degree,
                            void* stream);
+/* The same with HOST pointers (synchronous; staged through the device). */
+int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double angle_step,
+                          double arc_step, double min_degree, int32_t* stable, double* degree);
 
 /* Base-angle-actuated forward kinematics (not in the reference): the alpha
  * slots of `jv_base` hold the tube angles AT THE BASE (what the actuators set) instead of at the
@@ -215,6 +218,24 @@ int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, i
 /* The same generator on the host (no CUDA). */
 int ctr_fk_sample_joints_host(const ctr_robot_desc* desc, uint64_t seed, int64_t first_config,
                               int64_t B, double* jv);
+
+/* Sampling with the extension-length scale policies of transrotscale.h
+ * (getRandomJointValues(.., TransRotScale), section_i.h:338-347):
+ *   CTR_FK_SCALE_NONE          phi_s = Length_s * u
+ *   CTR_FK_SCALE_GAMMA         phi_s = Length_s * u^p0 (GammaCorrection, :106-122; lut_size > 1
+ *                              selects its LookUpSize-entry interpolated table)
+ *   CTR_FK_SCALE_PROPORTIONAL  ProportionalScale (:273-291): total extension steered towards
+ *                              MaxLength * U[p0, p1]
+ * jv is a DEVICE pointer for ctr_fk_sample_joints_scaled, a host pointer for the _host form. */
+#define CTR_FK_SCALE_NONE         0
+#define CTR_FK_SCALE_GAMMA        1
+#define CTR_FK_SCALE_PROPORTIONAL 2
+int ctr_fk_sample_joints_scaled(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B,
+                                int policy, double p0, double p1, int32_t lut_size, double* jv,
+                                void* stream);
+int ctr_fk_sample_joints_scaled_host(const ctr_robot_desc* desc, uint64_t seed, int64_t first_config,
+                                     int64_t B, int policy, double p0, double p1, int32_t lut_size,
+                                     double* jv);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */
 

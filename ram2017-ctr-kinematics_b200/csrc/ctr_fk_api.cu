@@ -405,6 +405,39 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
     return 0;
 }
 
+int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,
+                          double min_degree, int32_t* stable, double* degree)
+{
+    int rc = check_common(h, jv, B, CTR_FK_MODE_STEP, arc_step, 0);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    const size_t b_jv = sizeof(double) * (size_t)h->njv * (size_t)B, b_deg = sizeof(double) * (size_t)B,
+                 b_st = sizeof(int32_t) * (size_t)B;
+    char* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, b_jv + b_deg + b_st);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: allocation", e);
+    cudaStream_t st = h->streams[0];
+    double* d_jv = (double*)d;
+    double* d_deg = (double*)(d + b_jv);
+    int32_t* d_st = (int32_t*)(d + b_jv + b_deg);
+    e = cudaMemcpyAsync(d_jv, jv, b_jv, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = ctr_fk_stability_batch(h, d_jv, B, angle_step, arc_step, min_degree, d_st, d_deg, st);
+        if (rc == 0) {
+            if (stable) e = cudaMemcpyAsync(stable, d_st, b_st, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && degree) e = cudaMemcpyAsync(degree, d_deg, b_deg, cudaMemcpyDeviceToHost, st);
+        }
+    }
+    cudaError_t es = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: copy", e);
+    if (es != cudaSuccess) return cuda_fail("ctr_fk_stability_host: sync", es);
+    return 0;
+}
+
 int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mode, double step, int32_t nsamples,
                       double tol, int32_t max_iter, double* jv_tip, double* tip, int32_t* iters, int32_t* status,
                       void* stream)
@@ -437,22 +470,33 @@ int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mod
     return 0;
 }
 
-int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B, double* jv, void* stream)
+int ctr_fk_sample_joints_scaled(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B, int policy,
+                                double p0, double p1, int32_t lut_size, double* jv, void* stream)
 {
     if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
     if (B < 0 || first_config < 0) { set_error("negative batch size or offset"); return CTR_FK_E_ARG; }
+    if (policy < CTR_FK_SCALE_NONE || policy > CTR_FK_SCALE_PROPORTIONAL || !std::isfinite(p0) || !std::isfinite(p1) ||
+        lut_size < 0 || (policy == CTR_FK_SCALE_GAMMA && !(p0 > 0.0)) ||
+        (policy == CTR_FK_SCALE_PROPORTIONAL && !(p0 >= 0.0 && p1 >= p0 && p1 <= 1.0))) {
+        set_error("bad scale policy parameters");
+        return CTR_FK_E_ARG;
+    }
     if (B == 0) return 0;
     if (!jv) { set_error("null joint-value pointer"); return CTR_FK_E_NULL; }
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
-    SamplerTable tb;
-    make_sampler_table(&h->desc, &tb);
     SamplerArgs a;
-    a.seed = seed; a.first = first_config; a.B = B; a.njv = tb.njv; a.jv = jv;
-    for (int j = 0; j < 16; ++j) a.scale[j] = j < tb.njv ? tb.scale[j] : 0.0;
+    make_sampler_table(&h->desc, &a.tb);
+    a.tb.policy = policy; a.tb.p0 = p0; a.tb.p1 = p1; a.tb.lut_size = lut_size;
+    a.seed = seed; a.first = first_config; a.B = B; a.jv = jv;
     cudaError_t e = launch_sampler(a, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail("sampler kernel launch", e);
     return 0;
+}
+
+int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, int64_t B, double* jv, void* stream)
+{
+    return ctr_fk_sample_joints_scaled(h, seed, first_config, B, CTR_FK_SCALE_NONE, 1.0, 1.0, 0, jv, stream);
 }
 
 int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* stream)

@@ -2,7 +2,6 @@
 // histogram, counting sort), the device-side joint sampler and the FP64 peak probe.
 #include "ctr_fk_kernels.cuh"
 #include "ctr_fk_internal.h"
-#include "../host/ctr_sampler.h"
 
 namespace ctrk {
 
@@ -154,17 +153,29 @@ __global__ void __launch_bounds__(256)
 sampler_kernel(const __grid_constant__ SamplerArgs a)
 {
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;   // one thread per joint value
-    if (e >= a.B * a.njv) return;
-    const int64_t i = e / a.njv;
-    const int     j = (int)(e - i * a.njv);
-    a.jv[e] = a.scale[j] * sampler_u01(a.seed, (uint64_t)(a.first + i), (uint32_t)j);
+    if (e >= a.B * a.tb.njv) return;
+    const int64_t i = e / a.tb.njv;
+    const int     j = (int)(e - i * a.tb.njv);
+    a.jv[e] = a.tb.scale[j] * sampler_u01(a.seed, (uint64_t)(a.first + i), (uint32_t)j);
+}
+
+// scale policies couple the Phi slots of one configuration: one thread per configuration
+__global__ void __launch_bounds__(256)
+sampler_policy_kernel(const __grid_constant__ SamplerArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.B) return;
+    double q[CTR_FK_MAX_JV];
+    sample_config(a.tb, a.seed, (uint64_t)(a.first + i), q);
+    for (int j = 0; j < a.tb.njv; ++j) a.jv[i * a.tb.njv + j] = q[j];
 }
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st)
 {
-    const int64_t total = a.B * a.njv;
+    const int64_t total = a.B * a.tb.njv;
     if (total <= 0) return cudaSuccess;
-    sampler_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    if (a.tb.policy == 0) sampler_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    else                  sampler_policy_kernel<<<(unsigned)((a.B + 255) / 256), 256, 0, st>>>(a);
     count_launch();
     return cudaGetLastError();
 }

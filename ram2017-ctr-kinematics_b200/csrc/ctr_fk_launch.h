@@ -82,13 +82,15 @@ cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, in
 cudaError_t launch_bin_offsets(uint32_t* hist, int nbins, cudaStream_t st);   // in place: descending exclusive scan
 cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, int nbins, cudaStream_t st);
 
+}  // namespace ctrk
+#include "../host/ctr_sampler.h"
+namespace ctrk {
 struct SamplerArgs {
-    uint64_t seed;
-    int64_t  first;
-    int64_t  B;
-    int      njv;
-    double   scale[16];
-    double*  jv;
+    uint64_t     seed;
+    int64_t      first;
+    int64_t      B;
+    SamplerTable tb;
+    double*      jv;
 };
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_fp64_probe(int iters, int blocks, double* sink, cudaStream_t st);

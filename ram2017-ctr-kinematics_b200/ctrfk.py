@@ -17,6 +17,7 @@ MODE_STEP, MODE_NSAMPLE = 0, 1
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
+SCALE_NONE, SCALE_GAMMA, SCALE_PROPORTIONAL = 0, 1, 2
 SHOOT_OK, SHOOT_PHI_RANGE, SHOOT_SINGULAR, SHOOT_MAX_ITER = 0, 1, 2, 3
 
 
@@ -70,9 +71,14 @@ SYMBOLS = {
     "ctr_fk_jacobian_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P, _P]),
     "ctr_fk_jacobian_host": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P]),
     "ctr_fk_stability_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
+    "ctr_fk_stability_host": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P]),
     "ctr_fk_batch_base": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_double, C.c_int32,
                                     _P, _P, _P, _P, _P]),
     "ctr_fk_sample_joints": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
+    "ctr_fk_sample_joints_scaled": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
+                                              C.c_int32, _P, _P]),
+    "ctr_fk_sample_joints_scaled_host": (C.c_int, [C.POINTER(RobotDesc), C.c_uint64, C.c_int64, C.c_int64, C.c_int,
+                                                   C.c_double, C.c_double, C.c_int32, _P]),
     "ctr_fk_sample_joints_host": (C.c_int, [C.POINTER(RobotDesc), C.c_uint64, C.c_int64, C.c_int64, _P]),
     "ctr_fk_count_samples_host": (C.c_int, [C.POINTER(RobotDesc), _P, C.c_int64, C.c_int, C.c_double,
                                             C.c_int32, _P]),
@@ -209,14 +215,16 @@ class Engine:
         _check(load().ctr_fk_batch_base(self.handle, _ptr(jv_base), B, mode, step, nsamples, tol, max_iter,
                                         _ptr(jv_tip), _ptr(tip), _ptr(iters), _ptr(status), stream))
 
-    def sample_joints(self, seed, first, B, jv, stream=None):
-        _check(load().ctr_fk_sample_joints(self.handle, seed, first, B, _ptr(jv), stream))
+    def sample_joints(self, seed, first, B, jv, stream=None, policy=SCALE_NONE, p0=1.0, p1=1.0, lut_size=0):
+        _check(load().ctr_fk_sample_joints_scaled(self.handle, seed, first, B, policy, p0, p1, lut_size,
+                                                  _ptr(jv), stream))
 
 
-def sample_joints_host(desc, seed, first, B):
+def sample_joints_host(desc, seed, first, B, policy=SCALE_NONE, p0=1.0, p1=1.0, lut_size=0):
     import numpy as np
     jv = np.empty((B, desc.njoints), dtype=np.float64)
-    _check(load().ctr_fk_sample_joints_host(C.byref(desc), seed, first, B, jv.ctypes.data))
+    _check(load().ctr_fk_sample_joints_scaled_host(C.byref(desc), seed, first, B, policy, p0, p1, lut_size,
+                                                   jv.ctypes.data))
     return jv
 
 

@@ -358,15 +358,31 @@ int ctr_fk_desc_from_xml(const char* path, int32_t max_samples, ctr_robot_desc* 
     return 0;
 }
 
-int ctr_fk_sample_joints_host(const ctr_robot_desc* d, uint64_t seed, int64_t first, int64_t B, double* jv)
+static int check_policy(int policy, double p0, double p1, int32_t lut)
+{
+    if (policy < CTR_FK_SCALE_NONE || policy > CTR_FK_SCALE_PROPORTIONAL) return CTR_FK_E_ARG;
+    if (!std::isfinite(p0) || !std::isfinite(p1) || lut < 0) return CTR_FK_E_ARG;
+    if (policy == CTR_FK_SCALE_GAMMA && !(p0 > 0.0)) return CTR_FK_E_ARG;
+    if (policy == CTR_FK_SCALE_PROPORTIONAL && !(p0 >= 0.0 && p1 >= p0 && p1 <= 1.0)) return CTR_FK_E_ARG;
+    return 0;
+}
+
+int ctr_fk_sample_joints_scaled_host(const ctr_robot_desc* d, uint64_t seed, int64_t first, int64_t B, int policy,
+                                     double p0, double p1, int32_t lut_size, double* jv)
 {
     if (!d || !jv) { set_error("ctr_fk_sample_joints_host: null argument"); return CTR_FK_E_NULL; }
-    if (validate_desc(d) || B < 0) { set_error("ctr_fk_sample_joints_host: bad descriptor or B"); return CTR_FK_E_ARG; }
+    if (validate_desc(d) || B < 0 || first < 0) { set_error("ctr_fk_sample_joints_host: bad descriptor, B or offset"); return CTR_FK_E_ARG; }
+    if (check_policy(policy, p0, p1, lut_size)) { set_error("bad scale policy parameters"); return CTR_FK_E_ARG; }
     SamplerTable tb;
     make_sampler_table(d, &tb);
-    for (int64_t i = 0; i < B; ++i)
-        for (int j = 0; j < tb.njv; ++j) jv[i * tb.njv + j] = tb.scale[j] * sampler_u01(seed, (uint64_t)(first + i), (uint32_t)j);
+    tb.policy = policy; tb.p0 = p0; tb.p1 = p1; tb.lut_size = lut_size;
+    for (int64_t i = 0; i < B; ++i) sample_config(tb, seed, (uint64_t)(first + i), jv + i * tb.njv);
     return 0;
+}
+
+int ctr_fk_sample_joints_host(const ctr_robot_desc* d, uint64_t seed, int64_t first, int64_t B, double* jv)
+{
+    return ctr_fk_sample_joints_scaled_host(d, seed, first, B, CTR_FK_SCALE_NONE, 1.0, 1.0, 0, jv);
 }
 
 int ctr_fk_count_samples_host(const ctr_robot_desc* d, const double* jv, int64_t B, int mode, double step,

@@ -208,6 +208,27 @@ void Robot::calcJacobian(const VectorJ& jv, const std::size_t& ns, const double&
     if (rc) std::cerr << "ERROR: calcJacobian: " << ctr_fk_last_error() << std::endl;
 }
 
+bool Robot::calcStability(const VectorJ& jv, const double& angleStep, const double& arcStep)
+{
+    if (!engine_) { fool(__func__); return false; }                     // ctr_robot.cpp null-robot branch
+    int32_t st = 0;
+    int rc = ctr_fk_stability_host(engine_, jv.data(), 1, angleStep, arcStep, -1.0, &st, nullptr);
+    if (rc) std::cerr << "ERROR: calcStability: " << ctr_fk_last_error() << std::endl;
+    stable_ = (rc == 0 && st == 1);
+    return stable_;
+}
+
+double Robot::calcDegreeStability(const VectorJ& jv, const double& angleStep, const double& arcStep, const double& minDegree)
+{
+    if (!engine_) { fool(__func__); return 0.0; }
+    int32_t st = 0;
+    double deg = 0.0;
+    int rc = ctr_fk_stability_host(engine_, jv.data(), 1, angleStep, arcStep, minDegree, &st, &deg);
+    if (rc) std::cerr << "ERROR: calcDegreeStability: " << ctr_fk_last_error() << std::endl;
+    stable_ = (rc == 0 && st == 1);
+    return deg;
+}
+
 std::ostream& operator<<(std::ostream& os, const Robot& r)
 {
     if (!r.engine_) return os << "FOOL: no robot";

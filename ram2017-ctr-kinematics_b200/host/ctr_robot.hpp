@@ -78,6 +78,12 @@ public:
     int calcKinematicBatch(const double* jv, std::int64_t B, const std::size_t& nSamples, double* tip,
                            std::int32_t* nOut = nullptr, double* stepOut = nullptr, std::int32_t* status = nullptr);
 
+    // ctr_robot.h:118-119; the last result is kept for getStable() (robot_i.h:535)
+    bool   calcStability(const VectorJ& jv, const double& angleDiscretizationStep, const double& arcLengthStep);
+    double calcDegreeStability(const VectorJ& jv, const double& angleDiscretizationStep, const double& arcLengthStep,
+                               const double& minDegreeStability = -1.);
+    bool   getStable() const noexcept { return stable_; }
+
     // ctr_robot.h:122 (NSamples form, tip only)
     void calcJacobian(const VectorJ& jv, const std::size_t& nSamples, const double& fdTrans, const double& fdRot,
                       MatJacobian& jacobianTip);
@@ -113,6 +119,7 @@ private:
     ctr_fk_handle  engine_;
     int            device_;
     std::size_t    nsamples_;
+    bool           stable_ = true;
     std::vector<double> frames_;      // [max_samples][12]
     std::vector<double> radius_;      // [max_samples]
     std::vector<double> alpha_base_;

@@ -20,6 +20,14 @@ namespace ctrk {
 struct SamplerTable {
     int    njv;
     double scale[CTR_FK_MAX_JV];
+    // extension-length scale policies of transrotscale.h (applied to the Phi slots only)
+    int    policy;                       // CTR_FK_SCALE_*
+    double p0, p1;                       // gamma | (scale_min, scale_max)
+    int    lut_size;                     // GammaCorrection<Real, LookUpSize>; 0 = exact pow
+    int    nsec;
+    int    phi_slot[CTR_FK_MAX_SECTIONS];
+    double seg_len[CTR_FK_MAX_SECTIONS];
+    double total_len;
 };
 
 CTR_SAMPLER_HD uint64_t splitmix64(uint64_t z)
@@ -43,11 +51,90 @@ inline void make_sampler_table(const ctr_robot_desc* d, SamplerTable* t)
     const double two_pi_m = nextafter(2.0 * M_PI, 0.0);
     int j = 0;
     t->scale[j++] = two_pi_m;
+    t->total_len = 0.0;
     for (int s = 0; s < d->nsections; ++s) {
+        t->phi_slot[s] = j;
+        t->seg_len[s] = d->sec[s].length;
+        t->total_len += d->sec[s].length;             // m_OverallMaxLength, transrotscale.h:170
         t->scale[j++] = d->sec[s].length;
         for (int k = 0; k < d->sec[s].ntube; ++k) t->scale[j++] = two_pi_m;
     }
     t->njv = j;
+    t->nsec = d->nsections;
+    t->policy = 0; t->p0 = 1.0; t->p1 = 1.0; t->lut_size = 0;
+}
+
+// non-contracted arithmetic so that host and device produce the same bits
+CTR_SAMPLER_HD double s_mul(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+CTR_SAMPLER_HD double s_add(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+CTR_SAMPLER_HD double s_div(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// GammaCorrection::scaleTrans (transrotscale.h:106-122): pow(u, gamma), or its LookUpSize-entry
+// linearly interpolated table (table = pow(linspace(0,1), gamma) after one set_scale call).
+CTR_SAMPLER_HD double scale_gamma(double u, double gamma, int lut)
+{
+    if (lut <= 1) return pow(u, gamma);
+    const double x  = u * (double)(lut - 1);
+    const int    i0 = (int)floor(x);
+    const int    i1 = (int)ceil(x);
+    const double md = x - (double)i0;
+    const double f0 = pow((double)i0 / (double)(lut - 1), gamma);
+    const double f1 = pow((double)i1 / (double)(lut - 1), gamma);
+    return f1 * md + f0 * (1.0 - md);
+}
+
+// One configuration's joint vector under a scale policy.  ProportionalScale
+// (transrotscale.h:273-291) is sequential over the sections of one configuration (each draw
+// narrows the interval of the next so that the total extension hits a goal length) and takes the
+// goal of configuration i from the LAST-section draw of configuration i-1 (:286-288); with a
+// counter-based generator that draw is recomputed instead of carried, so configurations stay
+// independent.  Configuration 0 takes its goal from an extra slot (the reference uses std::rand).
+CTR_SAMPLER_HD void sample_config(const SamplerTable& t, uint64_t seed, uint64_t config, double* jv)
+{
+    for (int j = 0; j < t.njv; ++j) jv[j] = t.scale[j] * sampler_u01(seed, config, (uint32_t)j);
+    if (t.policy == 1) {                       // CTR_FK_SCALE_GAMMA
+        for (int s = 0; s < t.nsec; ++s) {
+            const int j = t.phi_slot[s];
+            jv[j] = t.seg_len[s] * scale_gamma(sampler_u01(seed, config, (uint32_t)j), t.p0, t.lut_size);
+        }
+    } else if (t.policy == 2) {                // CTR_FK_SCALE_PROPORTIONAL
+        const double ug = (config == 0) ? sampler_u01(seed, 0, 63u)
+                                        : sampler_u01(seed, config - 1, (uint32_t)t.phi_slot[t.nsec - 1]);
+        const double inst = s_add(s_mul(t.p1 - t.p0, ug), t.p0);
+        double goal = s_mul(t.total_len, inst), maxrem = t.total_len;
+        for (int s = 0; s < t.nsec; ++s) {
+            const int    j = t.phi_slot[s];
+            const double L = t.seg_len[s];
+            const double u = sampler_u01(seed, config, (uint32_t)j);
+            const double lo = fmax(s_div(s_add(s_add(goal, -maxrem), L), L), 0.0);
+            const double hi = fmin(s_div(goal, L), 1.0);
+            const double v  = s_add(s_mul(s_add(hi, -lo), u), lo);
+            goal = s_add(goal, -s_mul(v, L));
+            maxrem = s_add(maxrem, -L);
+            jv[j] = s_mul(L, fmin(fmax(v, 0.0), 1.0));   // Erl::clamp, :290
+        }
+    }
 }
 
 }  // namespace ctrk

@@ -235,13 +235,22 @@ def test_host_pointer_batch_and_single(ctrfk, oracle, robots, engines):
 
 
 def test_device_sampler_equals_host_sampler(ctrfk, robots, engines):
+    st = torch.cuda.current_stream().cuda_stream
     for name in util.ROBOT_FILES:
         d = robots[name]
         B = 10_000
         jv = torch.empty(B, d.njoints, dtype=torch.float64, device="cuda")
-        engines[name].sample_joints(util.SEEDS[name], 12345, B, jv, torch.cuda.current_stream().cuda_stream)
+        engines[name].sample_joints(util.SEEDS[name], 12345, B, jv, st)
         torch.cuda.synchronize()
         assert np.array_equal(jv.cpu().numpy(), ctrfk.sample_joints_host(d, util.SEEDS[name], 12345, B))
+        # scale policies: ProportionalScale is bit-identical (non-contracted arithmetic), the gamma
+        # policy differs by the pow() of CUDA's and glibc's libm (<= 2 ulp)
+        engines[name].sample_joints(5, 77, B, jv, st, policy=ctrfk.SCALE_PROPORTIONAL, p0=0.2, p1=0.9)
+        torch.cuda.synchronize()
+        assert np.array_equal(jv.cpu().numpy(), ctrfk.sample_joints_host(d, 5, 77, B, policy=ctrfk.SCALE_PROPORTIONAL, p0=0.2, p1=0.9))
+        engines[name].sample_joints(5, 77, B, jv, st, policy=ctrfk.SCALE_GAMMA, p0=1.7, lut_size=0)
+        torch.cuda.synchronize()
+        assert np.allclose(jv.cpu().numpy(), ctrfk.sample_joints_host(d, 5, 77, B, policy=ctrfk.SCALE_GAMMA, p0=1.7), rtol=1e-14, atol=0)
 
 
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
@@ -429,3 +438,34 @@ def test_base_angle_shooting(ctrfk, oracle, robots, engines, name, mode):
     dp, ang = util.pose_errors(o2["tip"][good], tip_np[good])
     assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
     assert it_np[ok].max() >= it_np[ok].min() + 5           # divergent iteration counts were absorbed
+
+
+def test_cpp_host_binary_config1(ctrfk, oracle, robots, dev):
+    """BASELINE config 1 through the C++14 host object (host/ctr_test.cpp, the counterpart of the
+    reference's ctr_test.cpp): construction-time FK (N = 3, ctr_static.h:248-252) and the joint
+    vector of `std::mt19937{}` + `uniform_real_distribution<double>{}` (ctr_test.cpp:30-32)."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(ctrfk.LIB_PATH), "ctr_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(ctrfk.LIB_PATH), "ctr_test"])
+    out = subprocess.run([exe, "256", ctrfk.resource("ctr_sec2_tub3.xml")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    d = robots["ctr_sec2_tub3.xml"]
+    m = re.search(r"construction FK: N=(\d+) tip=\(([^)]*)\)", out.stdout)
+    assert m and int(m.group(1)) == 3
+    tip0 = np.array([float(x) for x in m.group(2).split(",")])
+    r0 = oracle.fk_one(d, [0.0, 0.001, 0.0, 0.0, 0.001, 0.0], ctrfk.MODE_STEP, step=d.max_length / 256.0)
+    assert r0["n"] == 3 and np.abs(tip0 - r0["tip"][9:]).max() < util.TOL_POS
+    jv = np.array([float(x) for x in re.search(r"Joint values: (.*)", out.stdout).group(1).split()])
+    # libstdc++: mt19937 default seed 5489; generate_canonical<double,53> takes two 32-bit draws
+    rs = np.random.RandomState(5489)
+    raw = rs.randint(0, 2 ** 32, size=12, dtype=np.uint64)
+    u = [(float(raw[2 * i]) + float(raw[2 * i + 1]) * 4294967296.0) / 18446744073709551616.0 for i in range(6)]
+    c = np.nextafter(2 * np.pi, 0.0)
+    want = np.array([c * u[0], 0.06647 * u[1], c * u[2], c * u[3], 0.0667 * u[4], c * u[5]])
+    assert np.abs(jv - want).max() < 1e-15
+    m = re.search(r"FK: N=(\d+) tip=\(([^)]*)\)", out.stdout.split("Joint values")[1])
+    r1 = oracle.fk_one(d, jv, ctrfk.MODE_STEP, step=d.max_length / 256.0)
+    assert int(m.group(1)) == r1["n"]
+    assert np.abs(np.array([float(x) for x in m.group(2).split(",")]) - r1["tip"][9:]).max() < util.TOL_POS

@@ -184,3 +184,34 @@ def test_null_handle_and_bad_args(ctrfk):
     assert lib.ctr_fk_batch(None, None, 1, 0, 1e-3, 0, 0, None, None, None, None, None, None, None, None) == ctrfk.E_NULL
     assert lib.ctr_fk_destroy(None) == 0
     assert lib.ctr_fk_create(None, 0, None) == ctrfk.E_NULL
+
+
+def test_sampler_scale_policies(ctrfk, robots):
+    """transrotscale.h policies on the Phi slots (section_i.h:338-347)."""
+    d = robots["ctr_sec3_tub4.xml"]
+    B, seed = 4000, 9
+    base = ctrfk.sample_joints_host(d, seed, 0, B)
+    lens = np.array([0.06647, 0.0667, 0.01265]); phi = [1, 4, 6]
+    u = base[:, phi] / lens
+    # GammaCorrection without table: phi = L * u^gamma (transrotscale.h:120); other slots untouched
+    g = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_GAMMA, p0=2.5)
+    assert np.allclose(g[:, phi], lens * u ** 2.5, rtol=1e-14, atol=0)
+    rest = [j for j in range(d.njoints) if j not in phi]
+    assert np.array_equal(g[:, rest], base[:, rest])
+    # ... and with a 64-entry interpolated table (:113-117): close to the exact power, exact at the nodes
+    gl = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_GAMMA, p0=2.5, lut_size=64)
+    assert np.abs(gl[:, phi] / lens - u ** 2.5).max() < 2e-3
+    # ProportionalScale (:273-291): the total extension of configuration i hits
+    # MaxLength * (p0 + (p1-p0) * u_goal), u_goal = last-section draw of configuration i-1
+    p0, p1 = 0.3, 0.6
+    pr = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_PROPORTIONAL, p0=p0, p1=p1)
+    total = pr[:, phi].sum(axis=1)
+    goal = lens.sum() * (p0 + (p1 - p0) * u[:-1, 2])
+    assert np.abs(total[1:] - goal).max() < 1e-15
+    assert (pr[:, phi] >= 0).all() and (pr[:, phi] <= lens).all()
+    assert total[0] >= lens.sum() * p0 - 1e-15 and total[0] <= lens.sum() * p1 + 1e-15
+    # shards are independent
+    assert np.array_equal(ctrfk.sample_joints_host(d, seed, 100, 50, policy=ctrfk.SCALE_PROPORTIONAL, p0=p0, p1=p1), pr[100:150])
+    for bad in (dict(policy=7), dict(policy=ctrfk.SCALE_GAMMA, p0=-1.0), dict(policy=ctrfk.SCALE_PROPORTIONAL, p0=0.8, p1=0.2)):
+        with pytest.raises(ctrfk.CtrFkError):
+            ctrfk.sample_joints_host(d, seed, 0, 4, **bad)
