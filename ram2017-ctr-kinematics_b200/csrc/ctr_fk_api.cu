@@ -218,7 +218,10 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     std::lock_guard<std::mutex> lock(h->host_mu);
 
     constexpr int NS = ctr_fk_engine::kStreams;
-    const int64_t chunk = std::min<int64_t>(kHostChunk, B);
+    // one chunk = one full wave of the tip kernel (4 CTAs of kBlock threads per SM): a chunk that
+    // fills only part of the resident slots would pay a whole wave time for less work
+    const int64_t wave = (int64_t)h->sm_count * 4 * kBlock;
+    const int64_t chunk = std::min<int64_t>(wave > 0 ? wave : kHostChunk, B);
     const int njv = h->njv;
     // one slab per stream: jv | tip | n_out | step_out | status
     const size_t off_tip  = sizeof(double) * (size_t)chunk * njv;

@@ -469,3 +469,74 @@ def test_cpp_host_binary_config1(ctrfk, oracle, robots, dev):
     r1 = oracle.fk_one(d, jv, ctrfk.MODE_STEP, step=d.max_length / 256.0)
     assert int(m.group(1)) == r1["n"]
     assert np.abs(np.array([float(x) for x in m.group(2).split(",")]) - r1["tip"][9:]).max() < util.TOL_POS
+
+
+def random_robot(ctrfk, rng, ntubes, max_samples=128):
+    """A random but physically sensible robot with the given tubes-per-section layout."""
+    d = ctrfk.RobotDesc()
+    d.nsections = len(ntubes)
+    d.max_samples = max_samples
+    A = rng.normal(size=(3, 3))
+    Q, _ = np.linalg.qr(A)
+    if np.linalg.det(Q) < 0:
+        Q[:, 0] = -Q[:, 0]
+    t = list(Q.T.reshape(-1)) + list(rng.uniform(-0.1, 0.1, 3))        # column-major rotation + translation
+    for i in range(12):
+        d.init_trafo[i] = t[i]
+    for s, n in enumerate(ntubes):
+        d.sec[s].ntube = n
+        d.sec[s].length = rng.uniform(0.02, 0.08)
+        for k in range(n):
+            d.sec[s].stiffness[k] = rng.uniform(0.05, 6.0)
+            d.sec[s].curvature[k] = rng.uniform(1.0, 60.0)
+            d.sec[s].radius[k] = rng.uniform(3e-4, 2e-3)
+            d.sec[s].poisson[k] = rng.uniform(0.2, 0.45)               # distinct per tube: exercises the
+    return d                                                           # last-VC-section quirk (section_i.h:273)
+
+
+ALL_LAYOUTS = [(1,), (2,), (1, 1), (1, 2), (2, 1), (2, 2), (1, 1, 1), (1, 1, 2), (1, 2, 1), (1, 2, 2),
+               (2, 1, 1), (2, 1, 2), (2, 2, 1), (2, 2, 2)]
+
+
+@pytest.mark.parametrize("layout", ALL_LAYOUTS, ids=["-".join(map(str, l)) for l in ALL_LAYOUTS])
+def test_all_section_layouts(ctrfk, oracle, dev, layout):
+    """Every instantiated layout (1-3 sections of 1 or 2 tubes) with random parameters: tip, backbone,
+    radius, Jacobian tip, base angles — FAST and STRICT, both modes."""
+    rng = np.random.default_rng(hash(layout) % (2 ** 32))
+    d = random_robot(ctrfk, rng, layout)
+    eng = ctrfk.Engine(d, 0)
+    jv = np.vstack([ctrfk.sample_joints_host(d, 3, 0, 1500), util.edge_joint_sets(d)])
+    for mode, kw in ((1, dict(nsamples=128)), (0, dict(step=d.max_length / 100.0)), (1, dict(nsamples=2))):
+        o = oracle.fk_batch(d, jv, mode, backbone=True, radius=True, **kw)
+        for flags in (0, 1):
+            g = run_gpu(ctrfk, eng, jv, mode, flags=flags, backbone=True, radius=True, **kw)
+            assert_parity(o, g)
+            for i in range(0, jv.shape[0], 97):
+                n = o["n"][i]
+                dp, ang = util.pose_errors(o["backbone"][i, :n], g["backbone"][i, :n])
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+                assert np.array_equal(o["radius"][i, :n], g["radius"][i, :n])
+            t = run_gpu(ctrfk, eng, jv, mode, flags=flags, **kw)           # tip-only kernel
+            assert_parity(o, t)
+    eng.close()
+
+
+def test_large_max_samples(ctrfk, oracle, robots, dev):
+    """MaxSamples = 4096 (no binning histogram in shared memory beyond it, thread-per-configuration
+    backbone kernel above 1024) and N = 4096 sweeps."""
+    d = ctrfk.RobotDesc.from_buffer_copy(robots["ctr_sec3_tub5.xml"])
+    d.max_samples = 4096
+    eng = ctrfk.Engine(d, 0)
+    jv = ctrfk.sample_joints_host(d, 8, 0, 9000)
+    for mode, kw in ((1, dict(nsamples=4096)), (0, dict(step=d.max_length / 3000.0))):
+        o = oracle.fk_batch(d, jv, mode, **kw)
+        g = run_gpu(ctrfk, eng, jv, mode, **kw)
+        assert_parity(o, g)
+    small = jv[:40]
+    o = oracle.fk_batch(d, small, 1, nsamples=2048, backbone=True, radius=True)
+    g = run_gpu(ctrfk, eng, small, 1, nsamples=2048, backbone=True, radius=True)
+    assert_parity(o, g)
+    for i in range(0, 40, 7):
+        dp, ang = util.pose_errors(o["backbone"][i, :2048], g["backbone"][i, :2048])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+    eng.close()
