@@ -132,6 +132,8 @@ int ctr_fk_get_desc(ctr_fk_handle h, ctr_robot_desc* out);
  *   alpha_base[B][ntubes]             out, nullable: m_SampleTubeAlpha after the sweep (the tube
  *                                     angles at the base; what calcStability reads, robot_i.h:810)
  *   status    [B]                     out, nullable: CTR_FK_STATUS_* bits
+ * jv, tip and backbone must be 16-byte aligned (CTR_FK_E_ARG otherwise); a 32-byte aligned
+ * backbone buffer selects the fastest backbone kernel.
  */
 int ctr_fk_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                  int32_t nsamples, uint32_t flags,

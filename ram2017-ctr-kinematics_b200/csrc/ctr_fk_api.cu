@@ -62,6 +62,20 @@ int cuda_fail(const char* what, cudaError_t e)
     return (int)e;
 }
 
+// The kernels use 16-byte vector loads/stores on joint vectors (even joint counts), poses and
+// frames; device buffers from cudaMalloc / torch are 256-B aligned, sub-views may not be.
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// joint vectors are read as 16-byte pairs only when the joint count is even
+int check_align(ctr_fk_handle h, const void* jv, const void* tip, const void* backbone)
+{
+    if (((h->njv & 1) == 0 && !aligned16(jv)) || !aligned16(tip) || !aligned16(backbone)) {
+        set_error("joint-vector (even joint count), pose and backbone buffers must be 16-byte aligned");
+        return CTR_FK_E_ARG;
+    }
+    return 0;
+}
+
 int check_common(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples)
 {
     if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
@@ -201,6 +215,7 @@ int ctr_fk_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double 
 {
     int rc = check_common(h, jv, B, mode, step, nsamples);
     if (rc) return rc;
+    if ((rc = check_align(h, jv, tip, backbone))) return rc;
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     return run_batch(h, jv, B, mode, step, nsamples, flags, tip, backbone, radius, n_out, step_out,
@@ -224,11 +239,14 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     const int64_t chunk = std::min<int64_t>(wave > 0 ? wave : kHostChunk, B);
     const int njv = h->njv;
     // one slab per stream: jv | tip | n_out | step_out | status
-    const size_t off_tip  = sizeof(double) * (size_t)chunk * njv;
-    const size_t off_n    = off_tip + sizeof(double) * (size_t)chunk * 12;
-    const size_t off_step = off_n + sizeof(int32_t) * (size_t)chunk * 2;       // keeps 8-B alignment
-    const size_t off_stat = off_step + sizeof(double) * (size_t)chunk;
-    const size_t slab     = ((off_stat + sizeof(int32_t) * (size_t)chunk * 2 + 255) / 256) * 256;
+    // every sub-buffer starts on a 256-B boundary (the kernels use 16-B vector accesses; an odd
+    // joint count times an odd chunk would otherwise misalign the pose buffer)
+    auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t off_tip  = up256(sizeof(double) * (size_t)chunk * njv);
+    const size_t off_n    = off_tip + up256(sizeof(double) * (size_t)chunk * 12);
+    const size_t off_step = off_n + up256(sizeof(int32_t) * (size_t)chunk);
+    const size_t off_stat = off_step + up256(sizeof(double) * (size_t)chunk);
+    const size_t slab     = off_stat + up256(sizeof(int32_t) * (size_t)chunk);
     const int nslab = (int)std::min<int64_t>(NS, (B + chunk - 1) / chunk);
     // staging slabs are cached in the handle: cudaMalloc/cudaFree per call would add milliseconds
     // and a device-wide synchronisation to every batch
@@ -314,6 +332,7 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
 {
     int rc = check_common(h, jv, B, mode, step, nsamples);
     if (rc) return rc;
+    if ((rc = check_align(h, jv, tip, nullptr))) return rc;
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
@@ -339,6 +358,7 @@ int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t 
 {
     int rc = check_common(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples);
     if (rc) return rc;
+    if ((rc = check_align(h, jv, tip, nullptr))) return rc;
     if (!jac && B > 0) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
     if (!(fd_trans != 0.0) || !(fd_rot != 0.0) || !std::isfinite(fd_trans) || !std::isfinite(fd_rot)) {
         set_error("finite-difference steps must be finite and non-zero");
@@ -364,7 +384,9 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     const size_t njv = (size_t)h->njv;
-    const size_t b_jv = sizeof(double) * njv * (size_t)B, b_jac = sizeof(double) * 6 * njv * (size_t)B, b_tip = sizeof(double) * 12 * (size_t)B;
+    auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t b_jv = up256(sizeof(double) * njv * (size_t)B), b_jac = up256(sizeof(double) * 6 * njv * (size_t)B),
+                 b_tip = sizeof(double) * 12 * (size_t)B;
     char* d = nullptr;
     cudaError_t e = cudaMalloc((void**)&d, b_jv + b_jac + b_tip);
     if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: allocation", e);
@@ -372,11 +394,11 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
     double* d_jv = (double*)d;
     double* d_jac = (double*)(d + b_jv);
     double* d_tip = (double*)(d + b_jv + b_jac);
-    e = cudaMemcpyAsync(d_jv, jv, b_jv, cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(d_jv, jv, sizeof(double) * njv * (size_t)B, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         rc = ctr_fk_jacobian_batch(h, d_jv, B, nsamples, fd_trans, fd_rot, d_jac, tip ? d_tip : nullptr, st);
         if (rc == 0) {
-            e = cudaMemcpyAsync(jac, d_jac, b_jac, cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(jac, d_jac, sizeof(double) * 6 * njv * (size_t)B, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess && tip) e = cudaMemcpyAsync(tip, d_tip, b_tip, cudaMemcpyDeviceToHost, st);
         }
     }
@@ -393,6 +415,7 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
 {
     int rc = check_common(h, jv, B, CTR_FK_MODE_STEP, arc_step, 0);
     if (rc) return rc;
+    if ((rc = check_align(h, jv, nullptr, nullptr))) return rc;
     if (!(angle_step > 0.0) || !std::isfinite(angle_step) || !std::isfinite(min_degree)) {
         set_error("angle step must be finite and > 0, min_degree finite");
         return CTR_FK_E_ARG;
@@ -416,8 +439,9 @@ int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double a
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
-    const size_t b_jv = sizeof(double) * (size_t)h->njv * (size_t)B, b_deg = sizeof(double) * (size_t)B,
-                 b_st = sizeof(int32_t) * (size_t)B;
+    auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t n_jv = sizeof(double) * (size_t)h->njv * (size_t)B;
+    const size_t b_jv = up256(n_jv), b_deg = up256(sizeof(double) * (size_t)B), b_st = sizeof(int32_t) * (size_t)B;
     char* d = nullptr;
     cudaError_t e = cudaMalloc((void**)&d, b_jv + b_deg + b_st);
     if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: allocation", e);
@@ -425,12 +449,12 @@ int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double a
     double* d_jv = (double*)d;
     double* d_deg = (double*)(d + b_jv);
     int32_t* d_st = (int32_t*)(d + b_jv + b_deg);
-    e = cudaMemcpyAsync(d_jv, jv, b_jv, cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(d_jv, jv, n_jv, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         rc = ctr_fk_stability_batch(h, d_jv, B, angle_step, arc_step, min_degree, d_st, d_deg, st);
         if (rc == 0) {
             if (stable) e = cudaMemcpyAsync(stable, d_st, b_st, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess && degree) e = cudaMemcpyAsync(degree, d_deg, b_deg, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && degree) e = cudaMemcpyAsync(degree, d_deg, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st);
         }
     }
     cudaError_t es = cudaStreamSynchronize(st);
@@ -447,6 +471,7 @@ int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mod
 {
     int rc = check_common(h, jv_base, B, mode, step, nsamples);
     if (rc) return rc;
+    if ((rc = check_align(h, jv_base, tip, nullptr)) || (rc = check_align(h, jv_tip, nullptr, nullptr))) return rc;
     if (B > 0 && !jv_tip) { set_error("jv_tip output is required"); return CTR_FK_E_NULL; }
     if (!(tol > 0.0) || !std::isfinite(tol) || max_iter < 1) { set_error("tol must be > 0 and max_iter >= 1"); return CTR_FK_E_ARG; }
     if (B == 0) return 0;

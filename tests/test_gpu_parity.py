@@ -540,3 +540,65 @@ def test_large_max_samples(ctrfk, oracle, robots, dev):
         dp, ang = util.pose_errors(o["backbone"][i, :2048], g["backbone"][i, :2048])
         assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
     eng.close()
+
+
+def test_alignment_and_odd_sizes(ctrfk, oracle, robots, engines):
+    """Odd joint counts and odd batch sizes through the host-pointer paths (staging sub-buffers
+    must stay 16-byte aligned) and rejection of misaligned device views."""
+    name = "ctr_sec3_tub5.xml"                      # n_jv = 9
+    d = robots[name]
+    eng = engines[name]
+    B = 9001
+    jv = ctrfk.sample_joints_host(d, 12, 0, B)
+    tip = np.zeros((B, 12)); n = np.zeros(B, np.int32)
+    eng.batch_host(jv, B, 1, nsamples=32, tip=tip, n_out=n)
+    o = oracle.fk_batch(d, jv, 1, nsamples=32)
+    dp, ang = util.pose_errors(o["tip"], tip)
+    assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT and np.array_equal(n, o["n"])
+    jac = np.zeros((7, d.njoints, 6)); t7 = np.zeros((7, 12))
+    eng.jacobian_host(jv[:7], 7, 32, 1e-5, 1e-4, jac, t7)
+    assert np.abs(t7 - tip[:7]).max() < 1e-12
+    # a view that starts 8 bytes into an allocation is rejected, not faulted on
+    buf = torch.zeros(B * 12 + 1, dtype=torch.float64, device="cuda")
+    with pytest.raises(ctrfk.CtrFkError) as ei:
+        eng.batch(torch.from_numpy(jv).cuda(), B, 1, nsamples=8, tip=buf[1:])
+    assert ei.value.code == ctrfk.E_ARG
+
+
+def test_no_out_of_bounds_writes(ctrfk, robots, engines):
+    """compute-sanitizer is not available on this pool, so every output is placed between guard
+    bands filled with a sentinel; after all entry points ran, the bands must be untouched."""
+    name = "ctr_sec3_tub4.xml"
+    d = robots[name]
+    eng = engines[name]
+    B, G = 8999, 64                                     # odd batch above the binning threshold
+    maxs, T, NJ = d.max_samples, d.ntubes, d.njoints
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(numel, dtype):
+        buf = torch.full((numel + 2 * G,), -777, dtype=dtype, device="cuda")
+        return buf, buf[G:G + numel]
+
+    jv = torch.from_numpy(ctrfk.sample_joints_host(d, 6, 0, B)).cuda()
+    bufs = {k: guarded(n, t) for k, (n, t) in dict(
+        tip=(B * 12, torch.float64), bb=(B * maxs * 12, torch.float64), rad=(B * maxs, torch.float64),
+        n=(B, torch.int32), h=(B, torch.float64), ab=(B * T, torch.float64), stt=(B, torch.int32),
+        jac=(B * NJ * 6, torch.float64), jt=(B * NJ, torch.float64), it=(B, torch.int32),
+        deg=(B, torch.float64), smp=(B * NJ, torch.float64)).items()}
+    v = {k: b[1] for k, b in bufs.items()}
+    for mode, kw in ((1, dict(nsamples=256)), (0, dict(step=d.max_length / 256.0)), (1, dict(nsamples=1))):
+        for flags in (0, ctrfk.FLAG_STRICT, ctrfk.FLAG_SOA, ctrfk.FLAG_STRICT | ctrfk.FLAG_SOA, ctrfk.FLAG_NO_BINNING):
+            eng.batch(jv, B, mode, flags=flags, tip=v["tip"], backbone=v["bb"], radius=v["rad"], n_out=v["n"],
+                      step_out=v["h"], alpha_base=v["ab"], status=v["stt"], stream=st, **kw)
+            eng.batch(jv, B, mode, flags=flags, tip=v["tip"], radius=v["rad"], n_out=v["n"], step_out=v["h"],
+                      alpha_base=v["ab"], status=v["stt"], stream=st, **kw)
+        eng.batch_f32(jv, B, mode, tip=v["tip"], n_out=v["n"], step_out=v["h"], status=v["stt"], stream=st, **kw)
+        eng.batch_base(jv, B, mode, tol=1e-10, max_iter=5, jv_tip=v["jt"], tip=v["tip"], iters=v["it"],
+                       status=v["stt"], stream=st, **kw)
+    eng.jacobian(jv, B, 64, 1e-5, 1e-4, v["jac"], v["tip"], st)
+    eng.stability(jv, 700, 0.4, d.max_length / 64.0, -1.0, v["stt"], v["deg"], st)
+    eng.sample_joints(3, 5, B, v["smp"], st)
+    eng.sample_joints(3, 5, B, v["smp"], st, policy=ctrfk.SCALE_PROPORTIONAL, p0=0.1, p1=0.9)
+    torch.cuda.synchronize()
+    for k, (buf, view) in bufs.items():
+        assert bool((buf[:G] == -777).all()) and bool((buf[-G:] == -777).all()), "guard band of %s was written" % k
