@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--shoot", action="store_true", help="base-angle shooting solve (ctr_fk_batch_base) instead of FK")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer end-to-end leg (very large batches)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="configurations of the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -346,12 +347,14 @@ def main():
                                         "reference's algorithmic flops"})
 
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers) --------------------
-    h_jv = torch.empty(B, njv, dtype=torch.float64).pin_memory()
-    h_tip = torch.empty(B, 12, dtype=torch.float64).pin_memory()
-    h_jv.copy_(jvs[0].cpu())
+    do_e2e = not (a.backbone or a.f32 or a.shoot or a.no_e2e)
+    if do_e2e:
+        h_jv = torch.empty(B, njv, dtype=torch.float64).pin_memory()
+        h_tip = torch.empty(B, 12, dtype=torch.float64).pin_memory()
+        h_jv.copy_(jvs[0].cpu())
     # PCIe copy rates with the same pinned buffers: the bound of the end-to-end number
     pcie = {}
-    for name, dst, src in (("h2d_GBs", jvs[1], h_jv), ("d2h_GBs", h_tip, tips[1])):
+    for name, dst, src in ((("h2d_GBs", jvs[1], h_jv), ("d2h_GBs", h_tip, tips[1])) if do_e2e else ()):
         best = 0.0
         for _ in range(3):
             ev0.record()
@@ -361,7 +364,7 @@ def main():
             best = max(best, src.numel() * 8 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
         pcie[name] = best
     e2e = None
-    if not a.backbone and not a.f32 and not a.shoot:
+    if do_e2e:
         e2e_steps = max(3, min(a.steps, 10))
         for _ in range(2):
             eng.batch_host(h_jv, B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=h_tip)
