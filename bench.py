@@ -93,7 +93,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.ok:
@@ -338,7 +338,10 @@ def main():
                     "alg_bytes_per_launch": B * (njv * 8 + 96),
                     "peak_source": "measured live: independent-DFMA-chain probe on all SMs (ctr_fk_fp64_probe); "
                                    "MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
-                    "alg_flops_per_sample_step": fstep, "mean_samples": nsum / B}
+                    "alg_flops_per_sample_step": fstep, "mean_samples": nsum / B,
+                    # why this is not an HBM-bound kernel: algorithmic bytes over the same launch time
+                    "hbm": {"achieved_GBs": B * (njv * 8 + 96) / (kern_ms * 1e-3) / 1e9,
+                            "note": "about 1 % of the measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)"}}
 
     if a.f32:
         # the FP32 variant runs on the FP32 FMA pipe; no FP32 peak is measured here, so no fraction

@@ -96,9 +96,14 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                "libctrfk.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(or make -C ram2017-ctr-kinematics_b200); this package has no non-CUDA path")
+            # not a fallback: build the CUDA library in-tree (nvcc cross-compiles without a GPU)
+            import subprocess
+            try:
+                subprocess.check_call(["make", "-s", "-j", str(min(8, os.cpu_count() or 1)), "-C", HERE, "libctrfk.so"])
+            except Exception as e:
+                raise RuntimeError(
+                    "libctrfk.so is not built and `make -C ram2017-ctr-kinematics_b200` failed (%r); "
+                    "this package has no non-CUDA path" % (e,))
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
