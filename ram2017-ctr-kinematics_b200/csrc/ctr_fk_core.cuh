@@ -52,6 +52,9 @@ struct KRobot {
     double rk[kMaxSec];      // 1 / (ksum[s] + ... + ksum[S-1])       (FAST)
     double onu_last;         // 1 + nu of the innermost tube          (section_i.h:285)
     double cl;               // onu_last / ksum[S-1]                  (FAST)
+    double nczc[kMaxTube];   // -czc[t] * cl: torque balance of the innermost tube in one chain (FAST)
+    double kgr[kMaxSec][kMaxSec];   // kg[s] * rk[p], p <= s: curvature weight already divided by the
+                                    // stiffness of the active sections p..S-1               (FAST)
     double qini[4];          // unit quaternion (w,x,y,z) of the entry frame's rotation
     double ztol;
     int    maxs;
@@ -708,8 +711,18 @@ struct FastSweep {
     // hot form: tier-1 series, no branches; sxy and m precomputed by the caller
     CTR_HD void accumulate_hot(double ux, double uy, double uz, double sxy, double m)
     {
-        double qa, qb, qc;
-        se3_series4(m, qa, qb, qc);
+        // rotation series to full precision; the third-order translation term C = h^3 qc only
+        // needs ~1e-9 relative (it contributes ~1e-8 m per step), so qc stops after m^2
+        double qa = x_fma(CTRK_FC.qa4[0], m, CTRK_FC.qa4[1]);
+        double qb = x_fma(CTRK_FC.qb4[0], m, CTRK_FC.qb4[1]);
+        double qc = x_fma(CTRK_FC.qc4[2], m, CTRK_FC.qc4[3]);
+        qa = x_fma(qa, m, CTRK_FC.qa4[2]);
+        qb = x_fma(qb, m, CTRK_FC.qb4[2]);
+        qc = x_fma(qc, m, 1.0 / 6.0);
+        qa = x_fma(qa, m, CTRK_FC.qa4[3]);
+        qb = x_fma(qb, m, CTRK_FC.qb4[3]);
+        qa = x_fma(qa, m, 1.0);
+        qb = x_fma(qb, m, 1.0);
         const double b2 = kc.h * qb;
         const double b  = kc.hh * qb;
         const double ex = b * ux, ey = b * uy, ez = b * uz;
@@ -740,16 +753,17 @@ struct FastSweep {
             in_k[s] = (s == S - 1) ? true : le_nonneg(pos, c.end[s]);   // pos <= ArcEnd = End_{S-1}
             in_c[s] = in_k[s] && le_nonneg(c.start[s], pos);
         }
-        // 1 / (stiffness of the sections reaching this position): the active set is a suffix
-        double rks = rb.rk[S - 1];
-#pragma unroll
-        for (int s = S - 2; s >= 0; --s) rks = in_k[s] ? rb.rk[s] : rks;
-
+        // Curvature weights kappa_s K_s/n_s, already divided by the stiffness of the sections that
+        // reach this position.  End is non-decreasing in s, so the active set is a suffix
+        // {p..S-1}; section s is only ever weighted when it is active itself, i.e. p <= s.
         double cx = 0.0, cy = 0.0;
         bool first = true;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            const double g = in_c[s] ? rb.kg[s] : 0.0;
+            double gr = rb.kgr[s][s];
+#pragma unroll
+            for (int p2 = s - 1; p2 >= 0; --p2) gr = in_k[p2] ? rb.kgr[s][p2] : gr;
+            const double g = in_c[s] ? gr : 0.0;
 #pragma unroll
             for (int j = 0; j < L::nt(s); ++j) {
                 const int t = L::t0(s) + j;
@@ -760,8 +774,6 @@ struct FastSweep {
                 else       { cx = x_fma(-st, g, cx); cy = x_fma(ct, g, cy); }
             }
         }
-        cx *= rks;
-        cy *= rks;
         double uxs[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -784,15 +796,15 @@ struct FastSweep {
             // still has u_z = 0 (its update is masked by in_c, and in_c implies in_k), so the
             // in_k mask on the balance coefficients is redundant and dropped.
             if (T > 1) {
-                double cz = 0.0;
+                double zl = 0.0;          // innermost tube: -(sum czc_t z_t) * cl, coefficients pre-multiplied
 #pragma unroll
                 for (int t = T - 2; t >= 0; --t) {
                     const int s = L::sec_of(t);
                     const double hk = in_c[s] ? hko[t] : 0.0;
-                    cz     = (t == T - 2) ? rb.czc[t] * uzs[t] : x_fma(rb.czc[t], uzs[t], cz);
+                    zl     = (t == T - 2) ? rb.nczc[t] * uzs[t] : x_fma(rb.nczc[t], uzs[t], zl);
                     uzs[t] = x_fma(hk, uxs[t], uzs[t]);
                 }
-                uzs[T - 1] = -cz * rb.cl;
+                uzs[T - 1] = zl;
             } else {
                 uzs[0] = 0.0;      // -0 * cl, section_i.h:285 with an empty balance
             }

@@ -93,6 +93,7 @@ inline int make_krobot(const ctr_robot_desc* d, KRobot* r)
     const ctr_section_desc& last = d->sec[S - 1];
     r->onu_last = 1.0 + last.poisson[last.ntube - 1];
     r->cl       = r->onu_last / r->ksum[S - 1];
+    for (int tt = 0; tt < kMaxTube; ++tt) r->nczc[tt] = -r->czc[tt] * r->cl;
     for (int s = S - 1; s >= 0; --s) {
         // the reference accumulates front to back over the ACTIVE sections, which are always a
         // suffix {s..S-1} (End is non-decreasing); keep that order for the sum before inverting.
@@ -100,6 +101,8 @@ inline int make_krobot(const ctr_robot_desc* d, KRobot* r)
         for (int q = s; q < S; ++q) fwd += r->ksum[q];
         r->rk[s] = 1.0 / fwd;
     }
+    for (int s = 0; s < S; ++s)
+        for (int q = 0; q <= s; ++q) r->kgr[s][q] = r->kg[s] * r->rk[q];
     return 0;
 }
 
