@@ -131,7 +131,10 @@ def _check(rc):
 def resource(name):
     """Path of a robot XML shipped in tests/data (copies of nothing: generated by
     tests/golden/make_robot_xml.py from the parameter tables in SURVEY.md §9.2)."""
-    return os.path.join(REPO, "tests", "data", name)
+    path = os.path.join(REPO, "tests", "data", name)
+    if not os.path.exists(path) and name.startswith("ctr_"):      # BASELINE.json names the robots ctr_*.xml
+        path = os.path.join(REPO, "tests", "data", name[len("ctr_"):])
+    return path
 
 
 def desc_from_xml(path, max_samples=256, want_phi=False):
