@@ -164,6 +164,15 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
         set_error("ctr_fk_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
         return (int)cudaErrorNoKernelImageForDevice;
     }
+    {   // step mode and the shooting solve take stream-ordered temporaries; keep freed blocks in the
+        // device's default pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     ctr_fk_engine* h = new (std::nothrow) ctr_fk_engine;
     if (!h) { set_error("out of host memory"); return CTR_FK_E_NOMEM; }
     h->desc = *desc;
