@@ -602,3 +602,14 @@ def test_no_out_of_bounds_writes(ctrfk, robots, engines):
     torch.cuda.synchronize()
     for k, (buf, view) in bufs.items():
         assert bool((buf[:G] == -777).all()) and bool((buf[-G:] == -777).all()), "guard band of %s was written" % k
+
+
+def test_cpp_robot_selftest(ctrfk, dev):
+    """The C++14 host object (host/ctr_robot.hpp) through its own self-test binary."""
+    import subprocess
+    pkg = os.path.dirname(ctrfk.LIB_PATH)
+    exe = os.path.join(pkg, "robot_selftest")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", pkg, "robot_selftest"])
+    out = subprocess.run([exe, ctrfk.resource("ctr_sec2_tub3.xml")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
