@@ -242,7 +242,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <class L>
-__global__ void __launch_bounds__(kBbBlock)
+__global__ void __launch_bounds__(kBbBlock, 8)
 fk_backbone_warp_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     extern __shared__ __align__(16) double sh_park[];       // [kBbWarps][2][maxs*4]
@@ -317,13 +317,18 @@ fk_backbone_warp_kernel(const __grid_constant__ KRobot rb, const __grid_constant
             const StepConsts kc = make_step_consts(cf.h, rb.ztol);
 
             QT T = qt_identity();
+            bool allhot = true;       // every sample of this lane takes the branch-free forms below
             for (int k = k0; k < k1; ++k) {
                 const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
-                const double  uz = pk[4 * k + 2];
+                const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);
+                const double n2 = x_fma(v1.x, v1.x, x_fma(v0.y, v0.y, v0.x * v0.x));
+                allhot = allhot && le_nonneg(kc.ztol2, n2) && hi_word(n2 * kc.hh2) < 0x3f700000 &&
+                         (hi_word(v1.y + cf.theta) & 0x7fffffff) < 0x40900000;
                 QT E;
-                se3_step_fast_k(v0.x, v0.y, uz, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
+                se3_step_fast_k(v0.x, v0.y, v1.x, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
                 T = qt_mul(T, E);
             }
+            const bool hot_walk = __all_sync(0xffffffffu, allhot);
             // inclusive scan over lanes: T_l <- T_0 * ... * T_l
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -336,17 +341,44 @@ fk_backbone_warp_kernel(const __grid_constant__ KRobot rb, const __grid_constant
                 const double inv = rsqrt(I.w * I.w + I.x * I.x + I.y * I.y + I.z * I.z);
                 I.w *= inv; I.x *= inv; I.y *= inv; I.z *= inv;
             }
-            for (int k = k0; k < k1; ++k) {
-                const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
-                const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);   // (u_z, alpha_k)
-                QT E;
-                se3_step_fast_k(v0.x, v0.y, v1.x, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
-                I = qt_mul(I, E);
-                double shf, chf, F[12];
-                fast_sincos(0.5 * (v1.y + cf.theta), shf, chf);
-                qt_frame(rb, I, shf, chf, F);
-                store_tf256(slot0 + (int64_t)k * 12, F);
-                if (k == n - 1 && a.tip) store_tf(a.tip + cf.cfg * 12, F);
+            if (hot_walk) {
+                // branch-free body, two samples per trip: the step and the frame trigonometry of
+                // sample k+1 overlap the (serial) product and frame assembly of sample k
+#pragma unroll 2
+                for (int k = k0; k < k1; ++k) {
+                    const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
+                    const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);   // (u_z, alpha_k)
+                    const double sxy = x_fma(v0.y, v0.y, v0.x * v0.x);
+                    const double m   = x_fma(v1.x, v1.x, sxy) * kc.hh2;
+                    double qa, qb, qc;
+                    se3_series4(m, qa, qb, qc);
+                    const double b2 = kc.h * qb, b = kc.hh * qb;
+                    QT E;
+                    E.w = qa; E.x = b * v0.x; E.y = b * v0.y; E.z = b * v1.x;
+                    const double C = kc.h3 * qc, cz = C * v1.x;
+                    E.px = x_fma(cz, v0.x, b2 * E.y);
+                    E.py = x_fma(cz, v0.y, -(b2 * E.x));
+                    E.pz = x_fma(-C, sxy, kc.h);
+                    I = qt_mul(I, E);
+                    double shf, chf, F[12];
+                    sincos_bounded(0.5 * (v1.y + cf.theta), shf, chf);
+                    qt_frame(rb, I, shf, chf, F);
+                    store_tf256(slot0 + (int64_t)k * 12, F);
+                    if (k == n - 1 && a.tip) store_tf(a.tip + cf.cfg * 12, F);
+                }
+            } else {
+                for (int k = k0; k < k1; ++k) {
+                    const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
+                    const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);   // (u_z, alpha_k)
+                    QT E;
+                    se3_step_fast_k(v0.x, v0.y, v1.x, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
+                    I = qt_mul(I, E);
+                    double shf, chf, F[12];
+                    fast_sincos(0.5 * (v1.y + cf.theta), shf, chf);
+                    qt_frame(rb, I, shf, chf, F);
+                    store_tf256(slot0 + (int64_t)k * 12, F);
+                    if (k == n - 1 && a.tip) store_tf(a.tip + cf.cfg * 12, F);
+                }
             }
             if (a.radius) {
                 // robot_i.h:1286-1307, lanes striding over the samples of each section's run
