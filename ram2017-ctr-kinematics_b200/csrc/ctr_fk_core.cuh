@@ -14,9 +14,12 @@
 // Two arithmetic variants:
 //   STRICT  - every expression in the reference's operation order, libm-grade sin/cos/div/sqrt.
 //   FAST    - algebraically equivalent: reciprocals of per-section constants hoisted, the
-//             SE(3) step as power series in (h|u|)^2 (no sqrt, no division, no trig), rotation
-//             accumulated as a unit quaternion, custom sin/cos with 2-term Cody-Waite reduction.
-//             Differences to STRICT are O(1e-15) per step.
+//             SE(3) step as power series in (h|u|/2)^2 (no sqrt, no division, no trig), rotation
+//             accumulated as a unit quaternion, sin/cos of the tube angles carried and rotated by
+//             the per-step increment, software-pipelined sweep.  Differences to STRICT are
+//             O(1e-15) per step (measured end to end: DESIGN.md section 5).
+// Also here: the tangent-linear sweep and Newton step of the base-angle shooting solve, the
+// quaternion+translation helpers of the warp-parallel backbone pass, the radius fill.
 // Both use the SAME control scalars (sum of Phi, N, h, the arc-position sequence and the
 // section-interval compares), evaluated with non-contracted IEEE operations, because those decide
 // which samples exist (SURVEY.md §7 "bit-critical scalars").
@@ -501,9 +504,8 @@ CTR_HD void fast_sincos(double x, double& s_out, double& c_out)
 //   qc(m) = (t - sin t)/t^3, t = 2 sqrt m  = 1/6 - 4m/120 + 16 m^2/5040 - ...
 // Tier 1 (m <= 2^-8, i.e. h|u| <= 0.125 rad per step: every step of the benchmark workloads):
 // through m^4, truncation < 3e-19.  Tier 2 (m <= 2^-4): through m^7, truncation < 1e-18.
-constexpr double kFastM1 = 0.00390625;   // 2^-8
+constexpr double kFastM1 = 0.00390625;   // 2^-8 (tested on the bit pattern: hi word < 0x3f700000)
 constexpr double kFastM2 = 0.0625;       // 2^-4
-constexpr double kFastM  = kFastM2;
 
 CTR_HD void se3_series4(double m, double& qa, double& qb, double& qc)
 {
