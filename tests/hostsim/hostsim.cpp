@@ -110,3 +110,30 @@ extern "C" int hostsim_shoot(const ctr_robot_desc* d, const double* jvb, int64_t
     }
     return 0;
 }
+
+// tangent-linear sweep of one configuration: base angles and d base / d tip angles
+namespace {
+template <class L>
+int tangent_run(const KRobot& rb, const double* jv, int mode, double step, int ns, double* base, double* jac)
+{
+    Ctl<L> c;
+    setup_control<L>(rb, jv, mode, step, ns, c);
+    if (c.status) return 1;
+    sweep_tangent<L>(rb, c, base, L::T > 1 ? jac : nullptr);
+    return 0;
+}
+}  // namespace
+
+extern "C" int hostsim_tangent(const ctr_robot_desc* d, const double* jv, int mode, double step, int ns,
+                               double* base, double* jac)
+{
+    KRobot rb;
+    int rc = make_krobot(d, &rb);
+    if (rc) return rc;
+    switch (layout_key(d)) {
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: return tangent_run<Lay<S, A, Bq, C>>(rb, jv, mode, step, ns, base, jac);
+        CTRK_FOR_EACH_LAYOUT(X)
+#undef X
+        default: return CTR_FK_E_DESC;
+    }
+}

@@ -149,3 +149,30 @@ def test_shooting_solve_logic(ctrfk, oracle, hostsim, robots, name):
     idx = util.alpha_indices(d)
     assert np.array_equal(jt[:, [i for i in range(jv.shape[1]) if i not in idx[1:]]],
                           jv[:, [i for i in range(jv.shape[1]) if i not in idx[1:]]])   # only alphas 1.. change
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_tangent_sweep_jacobian(ctrfk, oracle, hostsim, robots, name):
+    """The variational Jacobian d(base angles)/d(tip angles) of the shooting solve against central
+    differences of the ORACLE's base angles, and its base angles against the oracle's."""
+    import ctypes as C
+    hostsim.hostsim_tangent.restype = C.c_int
+    hostsim.hostsim_tangent.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    d = robots[name]
+    T = d.ntubes
+    idx = util.alpha_indices(d)
+    jv = ctrfk.sample_joints_host(d, 21, 0, 25)
+    for q in jv:
+        for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=96)), (ctrfk.MODE_STEP, dict(step=d.max_length / 80.0))):
+            base = np.zeros(T); jac = np.zeros((T - 1, T - 1))
+            rc = hostsim.hostsim_tangent(C.addressof(d), q.ctypes.data, mode, kw.get("step", 0.0), kw.get("nsamples", 0),
+                                         base.ctypes.data, jac.ctypes.data)
+            assert rc == 0
+            o = oracle.fk_one(d, q, mode, **kw)
+            assert np.abs(base - o["alpha_base"]).max() < 1e-11
+            eps = 1e-6
+            for c in range(T - 1):
+                qp = q.copy(); qm = q.copy()
+                qp[idx[c + 1]] += eps; qm[idx[c + 1]] -= eps
+                fd = (oracle.fk_one(d, qp, mode, **kw)["alpha_base"][1:] - oracle.fk_one(d, qm, mode, **kw)["alpha_base"][1:]) / (2 * eps)
+                assert np.abs(jac[:, c] - fd).max() < 1e-6 * max(1.0, np.abs(fd).max()), (c, jac[:, c], fd)
