@@ -435,7 +435,14 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
     StabArgs a;
     a.jv = jv; a.B = B; a.angle_step = angle_step; a.arc_step = arc_step; a.min_degree = min_degree;
     a.stable = stable; a.degree = degree;
-    cudaError_t e = launch_stability(h->key, h->rb, a, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* ticket = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&ticket, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail("ticket allocation", e);
+    e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
+    a.ticket = ticket;
+    if (e == cudaSuccess) e = launch_stability(h->key, h->rb, a, h->sm_count, st);
+    cudaFreeAsync(ticket, st);
     if (e != cudaSuccess) return cuda_fail("stability kernel launch", e);
     return 0;
 }

@@ -112,10 +112,9 @@ cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStr
 }
 
 // ---- calcStability / calcDegreeStability (robot_i.h:756-899) -------------------------------------
-// One thread per configuration: for every tube 1..T-1 scan its tip angle and watch the tube's
-// base angle, which only needs the tip->base sweep (no frames).  The scan variable is advanced
-// and compared exactly like the reference (`scan += step; scan <= end`), because that decides
-// how many scan points exist.
+// For every tube 1..T-1 the tip angle is scanned and the tube's base angle watched, which only
+// needs the tip->base sweep (no frames).  The scan variable is advanced and compared exactly like
+// the reference (`scan += step; scan <= end`), because that decides how many scan points exist.
 template <class L>
 __device__ __forceinline__ bool base_angles(const KRobot& rb, const double* q, double arc_step, double* alb)
 {
@@ -126,70 +125,129 @@ __device__ __forceinline__ bool base_angles(const KRobot& rb, const double* q, d
     return true;
 }
 
+// The number of sweeps per configuration varies wildly (the scan length depends on the tip angle,
+// and an unstable configuration stops at the first decreasing step), so the kernel is persistent
+// with a ticket queue like the shooting solve: the unit of lock-step work is ONE sweep; a lane
+// that has finished its configuration draws the next index from a global counter.
 template <class L>
 __global__ void __launch_bounds__(kBlock)
 fk_stability_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ StabArgs a)
 {
     constexpr int T = L::T, NJ = L::NJ;
-    const int64_t cfg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (cfg >= a.B) return;
-    double q[NJ];
-    load_jv<L>(a.jv, cfg, q);
-    q[0] = 0.0;                                                        // robot_i.h:762
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * 3.14159265358979323846;
     const double dstep = a.angle_step;
-    bool   stable = true, valid = true;
-    bool   checked = !(a.min_degree > rb.ztol);                        // :834
-    double smallest = 1.7976931348623157e308;                          // numeric_limits<Real>::max()
-    double prev[T], cur[T];
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
-#pragma unroll 1
-    for (int t = 1; t < T && stable && valid; ++t) {
-        const int jp = 2 + L::sec_of(t) + t;
+    int64_t cfg = -1;
+    double  q[NJ];
+    int     t = 1;                       // tube being scanned
+    double  scan = 0.0, scan_end = 0.0, prev = 0.0, smallest = 0.0;
+    bool    have_prev = false, checked = false;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q[j] = 0.0;
+    bool drained = false;
+
+    auto start_tube = [&](int tube) {                                   // robot_i.h:782-791
+        const int jp = 2 + L::sec_of(tube) + tube;
         double tipa = 0.0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) tipa = (j == jp) ? q[j] : tipa;
-        double scan, scan_end;
-        if (tipa <= kPi) { scan = 0.0; scan_end = tipa; }              // :782-791
+        if (tipa <= kPi) { scan = 0.0; scan_end = tipa; }
         else             { scan = tipa; scan_end = kTwoPi; }
-        double qq[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) qq[j] = (j == jp) ? scan : q[j];
-        if (!base_angles<L>(rb, qq, a.arc_step, prev)) { valid = false; break; }
-        scan = x_add(scan, dstep);
-#pragma unroll 1
-        for (; scan <= scan_end; scan = x_add(scan, dstep)) {          // :802-813 / :870-891
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) qq[j] = (j == jp) ? scan : q[j];
-            base_angles<L>(rb, qq, a.arc_step, cur);
-            double rel = 0.0;
-#pragma unroll
-            for (int u = 0; u < T; ++u) rel = (u == t) ? cur[u] - prev[u] : rel;
-            if (rel < smallest) { checked = true; smallest = rel; }
-            if (rel < 0.0) { stable = false; break; }
-#pragma unroll
-            for (int u = 0; u < T; ++u) prev[u] = cur[u];
+        have_prev = false;
+    };
+    auto finish = [&](int stable_flag) {
+        if (a.stable) a.stable[cfg] = stable_flag;
+        if (a.degree) {
+            double deg;
+            if (stable_flag < 0) deg = qnan;
+            else if (checked) deg = atan2(dstep, smallest);             // :886, :897
+            else deg = a.min_degree + rb.ztol;                          // :898
+            a.degree[cfg] = deg;
         }
-    }
-    if (a.stable) a.stable[cfg] = valid ? (stable ? 1 : 0) : -1;
-    if (a.degree) {
-        double deg;
-        if (!valid) deg = __longlong_as_double(0x7ff8000000000000ll);
-        else if (checked) deg = atan2(dstep, smallest);                // :886, :897
-        else deg = a.min_degree + rb.ztol;                             // :898
-        a.degree[cfg] = deg;
+        cfg = -1;
+    };
+
+    for (;;) {
+        // ---- refill idle lanes ---------------------------------------------------------------
+        const bool need = (cfg < 0) && !drained;
+        const unsigned m = __ballot_sync(full, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long first = 0;
+            if (lane == leader) first = atomicAdd(a.ticket, (unsigned long long)__popc(m));
+            first = __shfl_sync(full, first, leader);
+            if (need) {
+                const int64_t idx = (int64_t)first + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.B) {
+                    cfg = idx;
+                    load_jv<L>(a.jv, cfg, q);
+                    q[0] = 0.0;                                          // robot_i.h:762
+                    checked = !(a.min_degree > rb.ztol);                 // :834
+                    smallest = 1.7976931348623157e308;
+                    t = 1;
+                    if (T > 1) start_tube(1);
+                }
+            }
+            if ((int64_t)first + __popc(m) >= a.B) drained = true;
+        }
+        if (__ballot_sync(full, cfg >= 0) == 0) break;
+        // ---- one sweep on every busy lane -------------------------------------------------------
+        if (cfg >= 0) {
+            if (T == 1) {                                               // nothing to scan
+                finish(1);
+            } else {
+                const int jp = 2 + L::sec_of(t) + t;
+                double qq[NJ], cur[T];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) qq[j] = (j == jp) ? scan : q[j];
+                if (!base_angles<L>(rb, qq, a.arc_step, cur)) {
+                    finish(-1);
+                } else {
+                    double cur_t = 0.0;
+#pragma unroll
+                    for (int u = 0; u < T; ++u) cur_t = (u == t) ? cur[u] : cur_t;
+                    bool unstable = false;
+                    if (have_prev) {                                    // :802-813 / :870-891
+                        const double rel = cur_t - prev;
+                        if (rel < smallest) { checked = true; smallest = rel; }
+                        unstable = rel < 0.0;
+                    }
+                    prev = cur_t;
+                    have_prev = true;
+                    if (unstable) {
+                        finish(0);
+                    } else {
+                        scan = x_add(scan, dstep);
+                        if (!(scan <= scan_end)) {                      // this tube is done
+                            ++t;
+                            if (t >= T) finish(1);
+                            else start_tube(t);
+                        }
+                    }
+                }
+            }
+        }
     }
 }
 
-cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, cudaStream_t st)
+cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, int sm_count, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((a.B + kBlock - 1) / kBlock);
+    cudaError_t e = cudaSuccess;
     switch (key) {
 #define X(S, A, Bq, C) \
-    case S * 1000 + A * 100 + Bq * 10 + C: \
-        fk_stability_kernel<Lay<S, A, Bq, C>><<<grid, kBlock, 0, st>>>(rb, a); \
-        break;
+    case S * 1000 + A * 100 + Bq * 10 + C: { \
+        int per_sm = 0; \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_stability_kernel<Lay<S, A, Bq, C>>, kBlock, 0); \
+        if (e != cudaSuccess) return e; \
+        if (per_sm < 1) per_sm = 1; \
+        int64_t want = (a.B + kBlock - 1) / kBlock; \
+        int64_t cap = (int64_t)per_sm * sm_count; \
+        fk_stability_kernel<Lay<S, A, Bq, C>><<<(unsigned)(want < cap ? want : cap), kBlock, 0, st>>>(rb, a); \
+        break; }
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X
         default: return cudaErrorInvalidValue;
