@@ -403,6 +403,204 @@ fk_backbone_warp_kernel(const __grid_constant__ KRobot rb, const __grid_constant
     }
 }
 
+// ---- backbone kernel, AoS layout, FAST arithmetic: checkpointed sweep, frames emitted per run ----
+// fk_backbone_warp_kernel moves 32 B per sample out to the output region in pass 1 and back in
+// pass 2, then needs two walks over the samples and a warp scan to turn them into frames.  Here
+// (scheme: ctr_fk_core.cuh, "frame emission from a checkpointed sweep"):
+//   pass 1  one thread per configuration runs the tip solver's sweep (suffix products carried,
+//           software-pipelined) and saves 32 records — sweep state + suffix product, 128-160 B —
+//           at the start of the configuration's own output region; sample N-1 is parked whole;
+//   pass 2  each warp takes the CTA's configurations one at a time; lane l repeats the sweep over
+//           its run of ceil(n/32) samples from record l and emits Frame_k as sample k appears
+//           (I_k = T inv(S_{k+1}), then I_{k-1} = I_k inv(E_k)).  No shared-memory staging, no
+//           scan, no second walk; a warp still writes one configuration's n*96 B region by itself,
+//           which keeps DRAM pages open (thread-per-configuration stores do not).
+// Round trip per configuration: 33 records (4-5 KB) instead of 16 KB of parked samples at N = 256.
+constexpr int kCkMinSamples = 128;      // below this the records are no smaller than parked samples
+#ifndef CTRK_BB_EXPERIMENT
+#define CTRK_BB_EXPERIMENT 0
+#endif
+#ifndef CTRK_CK_CTAS
+#define CTRK_CK_CTAS 8      // resident CTAs per SM the kernel is compiled for (register cap)
+#endif
+#ifndef CTRK_CK_WARPS
+#define CTRK_CK_WARPS 2
+#endif
+constexpr int kCkWarps = CTRK_CK_WARPS;
+constexpr int kCkBlock = kCkWarps * 32;
+
+struct EmShared {            // what pass 2 needs to know about a configuration
+    double  h, theta;
+    double  end[kMaxSec];
+    double  T[7];            // total product E_0 ... E_{frames-1}
+    int64_t cfg;
+    int     n, nframes;      // nframes = 0: nothing to do (invalid configuration or beyond the batch)
+    int     stop[kMaxSec];   // radius runs (robot_i.h:1286-1307): section s covers samples [stop[s-1], stop[s])
+};
+
+__device__ __forceinline__ void ld256cg(const double* p, double& a, double& b, double& c, double& d)
+{
+    asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+
+template <class L>
+struct RecStoreGlobal {      // CkptHook store: one record = EmitLayout<L>::kStride doubles
+    double* base;
+    template <class SW>
+    __device__ __forceinline__ void operator()(int slot, const SW& sw) const
+    {
+        constexpr int R = EmitLayout<L>::kStride;
+        double v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = 0.0;
+        sw.save_state(v);
+        sw.suffix_with_pending(v + EmitLayout<L>::kState);
+        double* p = base + (int64_t)slot * R;
+#pragma unroll
+        for (int g = 0; g < R; g += 4) st256(p + g, v[g], v[g + 1], v[g + 2], v[g + 3]);
+    }
+};
+struct HeadParkGlobal {      // on_sample of pass 1: only sample N-1 (the head step) is parked
+    double* dst;
+    int     nm1;
+    __device__ __forceinline__ void operator()(int k, double ux, double uy, double uz, double al) const
+    {
+        if (k == nm1) st256(dst, ux, uy, uz, al);
+    }
+};
+struct FrameStoreGlobal {    // emit_run store: 3 full sectors per frame
+    double* slot0;
+    double* tip;             // nullable
+    int     ktip;
+    __device__ __forceinline__ void operator()(int k, const double* F) const
+    {
+#if CTRK_BB_EXPERIMENT == 2      /* timing experiment: frames computed, (almost) never stored */
+        if (F[0] == 123.456) store_tf256(slot0 + (int64_t)k * 12, F);
+#else
+        store_tf256(slot0 + (int64_t)k * 12, F);
+#endif
+        if (k == ktip && tip) store_tf(tip, F);
+    }
+};
+
+template <class L>
+__global__ void __launch_bounds__(kCkBlock, CTRK_CK_CTAS)
+fk_backbone_emit_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
+{
+    constexpr int R = EmitLayout<L>::kStride;    // record stride, doubles
+    __shared__ EmShared sh[kCkBlock];
+    const int64_t i = (int64_t)blockIdx.x * kCkBlock + threadIdx.x;
+    EmShared me;
+    me.n = 0; me.nframes = 0; me.cfg = 0; me.h = 0.0; me.theta = 0.0;
+#pragma unroll
+    for (int s = 0; s < kMaxSec; ++s) { me.end[s] = 0.0; me.stop[s] = 0; }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) me.T[q] = 0.0;
+
+    // ---- pass 1: one thread per configuration, tip -> base sweep, 32 records saved --------------
+    if (i < a.B) {
+        const int64_t cfg = a.order ? (int64_t)a.order[i] : i;
+        double q[L::NJ];
+        load_jv<L>(a.jv, cfg, q);
+        Ctl<L> c;
+        setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
+        if (c.status) {
+            write_invalid<L>(a, cfg);
+        } else {
+            double* slot0 = a.backbone + cfg * 12 * (int64_t)rb.maxs;
+            const SegPlan plan(c.n, c.nframes);
+            CkptHook<RecStoreGlobal<L>> hook(plan, RecStoreGlobal<L>{slot0});
+            const HeadParkGlobal park{slot0 + 32 * R, c.n - 1};
+            FastSweep<L, true, HeadParkGlobal> sw(rb, c, park);
+            sw.run_hooked(hook);
+            if (a.n_out) a.n_out[cfg] = c.nframes;
+            if (a.step_out) a.step_out[cfg] = c.h;
+            if (a.alpha_base) {
+#pragma unroll
+                for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = sw.al[t];
+            }
+            if (a.status) a.status[cfg] = 0;
+            me.n = c.n; me.nframes = c.nframes; me.cfg = cfg; me.h = c.h; me.theta = c.theta;
+            me.T[0] = sw.Qw; me.T[1] = sw.Qx; me.T[2] = sw.Qy; me.T[3] = sw.Qz;
+            me.T[4] = sw.Px; me.T[5] = sw.Py; me.T[6] = sw.Pz;
+            int begin = 0;
+#pragma unroll
+            for (int s = 0; s < L::S; ++s) {
+                me.end[s] = c.end[s];
+                // robot_i.h:1295-1304: section s fills [begin, min(floor(End_s/h), n))
+                int stop = begin;
+                if (begin < c.nframes) {
+                    const double qd = x_div(c.end[s], c.h);
+                    stop = (qd >= 0.0 && qd < (double)c.nframes) ? (int)qd : c.nframes;
+                    if (stop < begin) stop = begin;
+                }
+                me.stop[s] = stop;
+                begin = stop;
+            }
+        }
+    }
+    sh[threadIdx.x] = me;
+    __syncthreads();        // records (global) and sh[] are visible to the whole CTA
+
+    // ---- pass 2: one warp per configuration ---------------------------------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if CTRK_BB_EXPERIMENT == 1      /* timing experiment: pass 1 only */
+    if (a.B > 0) return;
+#endif
+    for (int j = 0; j < 32; ++j) {
+        const EmShared& cf = sh[warp * 32 + j];
+        if (cf.nframes == 0) continue;                      // warp-uniform
+        const int n = cf.nframes;
+        const SegPlan plan(cf.n, n);
+        const int k0 = lane * plan.cnt;
+        const int k1 = (k0 + plan.cnt < n) ? k0 + plan.cnt : n;
+        double* slot0 = a.backbone + cf.cfg * 12 * (int64_t)rb.maxs;
+        {
+            Ctl<L> c;
+            c.theta = cf.theta; c.arc_end = 0.0; c.h = cf.h; c.n = cf.n; c.nframes = n; c.status = 0;
+#pragma unroll
+            for (int s = 0; s < L::S; ++s) {
+                c.end[s] = cf.end[s];
+                const double d = x_sub(c.end[s], rb.len[s]);     // as setup_control
+                c.start[s] = (0.0 < d) ? d : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < L::T; ++t) c.al[t] = 0.0;
+            double rec[R], head[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int g = 0; g < R; ++g) rec[g] = 0.0;
+            if (k0 < n) {
+                const bool holds_head = (k1 - 1 == cf.n - 1);
+                if (holds_head) ld256cg(slot0 + 32 * R, head[0], head[1], head[2], head[3]);
+                if ((holds_head ? cf.n - 2 : k1 - 1) >= k0) {
+#pragma unroll
+                    for (int g = 0; g < R; g += 4) ld256cg(slot0 + (int64_t)lane * R + g, rec[g], rec[g + 1], rec[g + 2], rec[g + 3]);
+                }
+            }
+            __syncwarp();       // every lane holds its record: the frames may now overwrite that region
+            QT T;
+            T.w = cf.T[0]; T.x = cf.T[1]; T.y = cf.T[2]; T.z = cf.T[3]; T.px = cf.T[4]; T.py = cf.T[5]; T.pz = cf.T[6];
+            emit_run<L>(rb, c, plan, lane, rec, head, T,
+                        FrameStoreGlobal{slot0, a.tip ? a.tip + cf.cfg * 12 : nullptr, n - 1});
+        }
+        if (a.radius) {
+            double* rad = a.radius + cf.cfg * (int64_t)rb.maxs;
+            int    begin = 0;
+            double rsec  = 0.0;
+#pragma unroll
+            for (int s = 0; s < L::S; ++s) {
+                if (begin >= n) continue;
+                rsec = rb.rad[s];
+                const int stop = cf.stop[s];
+                for (int k = begin + lane; k < stop; k += 32) rad[k] = rsec;
+                begin = stop;
+            }
+            __syncwarp();
+            if (lane == 0) rad[n - 1] = rsec;
+        }
+    }
+}
+
 #define CTRK_LAUNCH_CASE(KERNEL, FASTV, S, A, Bq, C)                                              \
     case S * 1000 + A * 100 + Bq * 10 + C:                                                        \
         KERNEL<Lay<S, A, Bq, C>, FASTV><<<grid, kBlock, 0, st>>>(rb, a);                          \

@@ -26,7 +26,23 @@ cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cud
     if (a.B <= 0) return cudaSuccess;
     const unsigned grid = grid_for(a.B);
     // AoS: warp-parallel second pass (needs a 32-B aligned buffer for its 256-bit stores)
-    if (!a.soa && rb.maxs <= kBbMaxSamples && (reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0) {
+    const bool warp_ok = !a.soa && rb.maxs <= kBbMaxSamples && (reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0;
+    // long backbones: checkpointed sweep, frames emitted per run (no per-sample parking round trip)
+    if (warp_ok && rb.maxs >= kCkMinSamples) {
+        const unsigned gridw = (unsigned)((a.B + kCkBlock - 1) / kCkBlock);
+        switch (key) {
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: \
+        fk_backbone_emit_kernel<Lay<S, A, Bq, C>><<<gridw, kCkBlock, 0, st>>>(rb, a); \
+        break;
+            CTRK_FOR_EACH_LAYOUT_K(X)
+#undef X
+            default: return cudaErrorInvalidValue;
+        }
+        count_launch();
+        return cudaGetLastError();
+    }
+    if (warp_ok) {
         const unsigned gridw = (unsigned)((a.B + kBbBlock - 1) / kBbBlock);
         const size_t smem = sizeof(double) * 4 * (size_t)rb.maxs * kBbBufs * kBbWarps;
         switch (key) {

@@ -176,3 +176,63 @@ def test_tangent_sweep_jacobian(ctrfk, oracle, hostsim, robots, name):
                 qp[idx[c + 1]] += eps; qm[idx[c + 1]] -= eps
                 fd = (oracle.fk_one(d, qp, mode, **kw)["alpha_base"][1:] - oracle.fk_one(d, qm, mode, **kw)["alpha_base"][1:]) / (2 * eps)
                 assert np.abs(jac[:, c] - fd).max() < 1e-6 * max(1.0, np.abs(fd).max()), (c, jac[:, c], fd)
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_checkpointed_resweep_reproduces_the_sweep(ctrfk, hostsim, robots, name):
+    """The backbone kernel's scheme: sweep once saving 32 states, repeat each run of samples from
+    its state.  The repeated samples must equal the straight sweep's (the only difference is that
+    a resumed run re-evaluates sin/cos of the carried angles: a few ulp)."""
+    import ctypes as C
+    d = robots[name]
+    jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name], 0, 400), util.edge_joint_sets(d)])
+    B = jv.shape[0]
+    hostsim.hostsim_resweep.restype = C.c_int
+    hostsim.hostsim_resweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    for mode, step, ns in ((ctrfk.MODE_NSAMPLE, 0.0, 256), (ctrfk.MODE_STEP, d.max_length / 256.0, 0),
+                           (ctrfk.MODE_NSAMPLE, 0.0, 1), (ctrfk.MODE_NSAMPLE, 0.0, 2), (ctrfk.MODE_NSAMPLE, 0.0, 31),
+                           (ctrfk.MODE_NSAMPLE, 0.0, 33), (ctrfk.MODE_NSAMPLE, 0.0, 64), (ctrfk.MODE_NSAMPLE, 0.0, 65),
+                           (ctrfk.MODE_NSAMPLE, 0.0, 225), (ctrfk.MODE_STEP, 0.004, 0), (ctrfk.MODE_STEP, 0.03, 0)):
+        ref = np.full((B, d.max_samples, 4), np.nan)
+        tip = np.zeros((B, 12)); n = np.zeros(B, np.int32); st = np.zeros(B); ab = np.zeros((B, 8))
+        assert hostsim.hostsim_fk(C.addressof(d), jv.ctypes.data, B, mode, step, ns, 1, tip.ctypes.data, n.ctypes.data,
+                                  st.ctypes.data, ab.ctypes.data, ref.ctypes.data) == 0
+        got = np.full((B, d.max_samples, 4), np.nan)
+        assert hostsim.hostsim_resweep(C.addressof(d), jv.ctypes.data, B, mode, step, ns, got.ctypes.data) == 0
+        for i in range(B):
+            nf = n[i]
+            assert np.isfinite(got[i, :nf]).all(), (mode, step, ns, i)
+            assert np.isnan(got[i, nf + 1:]).all()            # nothing beyond the sweep
+            err = np.abs(got[i, :nf] - ref[i, :nf])
+            # curvature relative to the largest component (sin/cos of an angle near 0 carries the
+            # absolute drift of the rotated pair: ~N ulp of 1), angles absolute
+            scale = max(1.0, np.abs(ref[i, :nf, :3]).max())
+            assert (err[:, :3] / scale).max() < 1e-12, (mode, step, ns, i, (err[:, :3] / scale).max())
+            assert err[:, 3].max() < 1e-12, (mode, step, ns, i, err[:, 3].max())
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_frame_emission_from_checkpoints_matches_oracle(ctrfk, oracle, hostsim, robots, name):
+    """emit_run (ctr_fk_core.cuh): frames rebuilt per run as T inv(S) and walked downwards must be
+    the oracle's frames — every frame, not only the tip."""
+    import ctypes as C
+    d = robots[name]
+    jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name] + 5, 0, 300), util.edge_joint_sets(d)])
+    B = jv.shape[0]
+    hostsim.hostsim_emit.restype = C.c_int
+    hostsim.hostsim_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    for mode, step, ns in ((ctrfk.MODE_NSAMPLE, 0.0, 256), (ctrfk.MODE_STEP, d.max_length / 256.0, 0),
+                           (ctrfk.MODE_NSAMPLE, 0.0, 1), (ctrfk.MODE_NSAMPLE, 0.0, 2), (ctrfk.MODE_NSAMPLE, 0.0, 31),
+                           (ctrfk.MODE_NSAMPLE, 0.0, 33), (ctrfk.MODE_NSAMPLE, 0.0, 64), (ctrfk.MODE_NSAMPLE, 0.0, 65),
+                           (ctrfk.MODE_NSAMPLE, 0.0, 225), (ctrfk.MODE_STEP, 0.004, 0), (ctrfk.MODE_STEP, 0.03, 0)):
+        o = oracle.fk_batch(d, jv, mode, step=step, nsamples=ns, backbone=True)
+        got = np.full((B, d.max_samples, 12), np.nan)
+        assert hostsim.hostsim_emit(C.addressof(d), jv.ctypes.data, B, mode, step, ns, got.ctypes.data) == 0
+        worst_p = worst_r = 0.0
+        for i in range(B):
+            nf = int(o["n"][i])
+            assert np.isfinite(got[i, :nf]).all(), (mode, step, ns, i)
+            assert np.isnan(got[i, nf:]).all(), (mode, step, ns, i)       # nothing beyond the last frame
+            dp, ang = util.pose_errors(o["backbone"][i, :nf], got[i, :nf])
+            worst_p = max(worst_p, dp.max()); worst_r = max(worst_r, ang.max())
+        assert worst_p < 2e-10 and worst_r < 1e-11, (mode, step, ns, worst_p, worst_r)
