@@ -421,7 +421,7 @@ constexpr int kCkMinSamples = 128;      // below this the records are no smaller
 #define CTRK_BB_EXPERIMENT 0
 #endif
 #ifndef CTRK_CK_CTAS
-#define CTRK_CK_CTAS 8      // resident CTAs per SM the kernel is compiled for (register cap)
+#define CTRK_CK_CTAS 6      // resident CTAs per SM the kernel is compiled for: 168 registers, 12 warps/SM (2-3 % faster than 128 registers x 16 warps; tools/tune_bb.cu)
 #endif
 #ifndef CTRK_CK_WARPS
 #define CTRK_CK_WARPS 2
