@@ -542,6 +542,30 @@ def test_large_max_samples(ctrfk, oracle, robots, dev):
     eng.close()
 
 
+@pytest.mark.parametrize("max_samples", [32, 64, 127, 128, 160, 1024])
+def test_backbone_kernel_variants(ctrfk, oracle, robots, dev, max_samples):
+    """AoS backbone across MaxSamples: per-sample parking kernel below 128, checkpointed sweep with
+    per-run frame emission from 128 to 1024 (runs of 4, 5 and 32 samples per lane), every frame of
+    every configuration; step mode includes dropped tip samples and short sweeps (idle lanes)."""
+    for name in ("ctr_sec3_tub5.xml", "ctr_sec2_tub3.xml"):
+        d = ctrfk.RobotDesc.from_buffer_copy(robots[name])
+        d.max_samples = max_samples
+        eng = ctrfk.Engine(d, 0)
+        jv = np.vstack([ctrfk.sample_joints_host(d, 77, 0, 700), util.edge_joint_sets(d)])
+        for mode, kw in ((1, dict(nsamples=max_samples)), (0, dict(step=d.max_length / max_samples)),
+                         (1, dict(nsamples=max_samples - 1)), (1, dict(nsamples=33)), (1, dict(nsamples=1))):
+            o = oracle.fk_batch(d, jv, mode, backbone=True, radius=True, **kw)
+            g = run_gpu(ctrfk, eng, jv, mode, backbone=True, radius=True, **kw)
+            assert_parity(o, g)
+            for i in range(jv.shape[0]):
+                n = o["n"][i]
+                dp, ang = util.pose_errors(o["backbone"][i, :n], g["backbone"][i, :n])
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT, (name, mode, kw, i)
+                assert np.array_equal(o["radius"][i, :n], g["radius"][i, :n])
+                assert np.array_equal(g["backbone"][i, n - 1], g["tip"][i])
+        eng.close()
+
+
 def test_alignment_and_odd_sizes(ctrfk, oracle, robots, engines):
     """Odd joint counts and odd batch sizes through the host-pointer paths (staging sub-buffers
     must stay 16-byte aligned) and rejection of misaligned device views."""
