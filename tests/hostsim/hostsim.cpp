@@ -7,7 +7,7 @@
 
 #include "../../include/ctr_fk.h"
 #include "../../ram2017-ctr-kinematics_b200/csrc/ctr_fk_krobot.h"
-#include "../../ram2017-ctr-kinematics_b200/csrc/ctr_fk_core_f32.cuh"
+#include "../../ram2017-ctr-kinematics_b200/csrc/ctr_fk_core_f32x2.cuh"
 
 using namespace ctrk;
 
@@ -25,6 +25,25 @@ template <class L>
 void run(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, int fast, double* tip,
          int32_t* n_out, double* step_out, double* alpha_base, double* samples)
 {
+    if (fast == 3) {        // packed FP32 variant: configurations (2i, 2i+1) as one pair, fixed-N mode
+        for (int64_t i = 0; i < B; i += 2) {
+            Ctl<L> c0, c1;
+            setup_control<L>(rb, jv + i * L::NJ, mode, step, ns, c0);
+            const bool has1 = i + 1 < B;
+            if (has1) setup_control<L>(rb, jv + (i + 1) * L::NJ, mode, step, ns, c1); else c1 = c0;
+            if (n_out) { n_out[i] = c0.nframes; if (has1) n_out[i + 1] = c1.nframes; }
+            if (step_out) { step_out[i] = c0.h; if (has1) step_out[i + 1] = c1.h; }
+            const bool ok0 = c0.status == 0, ok1 = has1 && c1.status == 0;
+            if (!ok0 && !ok1) continue;
+            double t0[12], t1[12];
+            if (!ok0) c0 = c1;
+            if (!ok1) c1 = c0;
+            solve_f32x2<L>(rb, c0, c1, ok0 ? t0 : nullptr, ok1 ? t1 : nullptr);
+            if (tip && ok0) std::memcpy(tip + 12 * i, t0, sizeof t0);
+            if (tip && ok1) std::memcpy(tip + 12 * (i + 1), t1, sizeof t1);
+        }
+        return;
+    }
     for (int64_t i = 0; i < B; ++i) {
         Ctl<L> c;
         setup_control<L>(rb, jv + i * L::NJ, mode, step, ns, c);

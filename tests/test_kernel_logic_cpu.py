@@ -121,6 +121,14 @@ def test_f32_solver_logic(ctrfk, oracle, hostsim, robots, name):
         assert np.array_equal(o["n"], s["n"]) and np.array_equal(o["step"], s["step"])
         dp, ang = util.pose_errors(o["tip"], s["tip"])
         assert dp.max() < TOL_F32_POS and ang.max() < TOL_F32_ROT, (dp.max(), ang.max())
+        if mode == ctrfk.MODE_NSAMPLE:
+            # packed variant (two configurations per thread, solve_f32x2), odd batch: last pair is half empty
+            for jvp in (jv, jv[:4999]):
+                op = {k: v[:jvp.shape[0]] for k, v in o.items()}
+                p = util.hostsim_fk(hostsim, d, jvp, mode, fast=3, **kw)
+                assert np.array_equal(op["n"], p["n"]) and np.array_equal(op["step"], p["step"])
+                dp, ang = util.pose_errors(op["tip"], p["tip"])
+                assert dp.max() < TOL_F32_POS and ang.max() < TOL_F32_ROT, ("packed", dp.max(), ang.max())
 
 
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
