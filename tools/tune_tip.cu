@@ -79,6 +79,11 @@ int main()
     CK(cudaMemcpy(djv, jv.data(), sizeof(double) * B * 6, cudaMemcpyHostToDevice));
     a.jv = djv; a.B = B; a.mode = 1; a.nsamples = 256; a.tip = dtip;
     run<128, 4>(rb, a, "base");
+    run<128, 3>(rb, a, "");
+    run<64, 7>(rb, a, "");
+    run<64, 6>(rb, a, "");
+    run<32, 14>(rb, a, "");
+    run<32, 13>(rb, a, "");
     run<128, 5>(rb, a, "");
     run<128, 6>(rb, a, "");
     run<64, 8>(rb, a, "");
