@@ -308,7 +308,9 @@ int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int3
     std::lock_guard<std::mutex> lock(h->host_mu);
     const size_t maxs = (size_t)h->rb.maxs;
     // layout (doubles): jv[16] | tip[12] | step[1] | alpha[8] | n,status (1 double) | radius[maxs] | backbone[12 maxs]
-    const size_t o_tip = 16, o_step = 28, o_al = 29, o_n = 37, o_rad = 38, o_bb = 38 + maxs;
+    // the frames start on a 32-byte boundary (the kernels store them with 16- and 32-byte vectors;
+    // an odd MaxSamples would otherwise leave them 8-byte aligned)
+    const size_t o_tip = 16, o_step = 28, o_al = 29, o_n = 37, o_rad = 38, o_bb = (38 + maxs + 3) / 4 * 4;
     const size_t total = (o_bb + 12 * maxs) * sizeof(double);
     cudaError_t e;
     if (!h->single_buf && (e = cudaMalloc((void**)&h->single_buf, total)) != cudaSuccess)

@@ -566,6 +566,24 @@ def test_backbone_kernel_variants(ctrfk, oracle, robots, dev, max_samples):
         eng.close()
 
 
+def test_single_configuration_with_odd_max_samples(ctrfk, oracle, robots, dev):
+    """ctr_fk_single keeps its frames behind a radius array of MaxSamples doubles: an odd MaxSamples
+    must not misalign them."""
+    for maxs in (127, 255, 33):
+        d = ctrfk.RobotDesc.from_buffer_copy(robots["ctr_sec3_tub4.xml"])
+        d.max_samples = maxs
+        eng = ctrfk.Engine(d, 0)
+        q = ctrfk.sample_joints_host(d, 3, 0, 1)[0]
+        t = np.zeros(12); bb = np.zeros((maxs, 12)); rd = np.zeros(maxs)
+        n = eng.single(q, 1, nsamples=maxs, tip=t, backbone=bb, radius=rd)
+        o = oracle.fk_batch(d, q[None, :], 1, nsamples=maxs, backbone=True, radius=True)
+        nn = int(o["n"][0])
+        dp, ang = util.pose_errors(o["backbone"][0, :nn], bb[:nn])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+        assert np.array_equal(o["radius"][0, :nn], rd[:nn])
+        eng.close()
+
+
 def test_alignment_and_odd_sizes(ctrfk, oracle, robots, engines):
     """Odd joint counts and odd batch sizes through the host-pointer paths (staging sub-buffers
     must stay 16-byte aligned) and rejection of misaligned device views."""
