@@ -1098,13 +1098,13 @@ CTR_HD void sweep_tangent(const KRobot& rb, const Ctl<L>& c, double* base, doubl
 #pragma unroll
     for (int t = 0; t + 1 < T; ++t) hko[t] = c.h * rb.onu[t] * rb.kappa[L::sec_of(t)];
     double pos = c.arc_end;
+    // sin/cos of the tube angles are carried and rotated by the step increment like in FastSweep
+    // (re-evaluated when an increment is large); tube 0 is pinned to 0 after the first step
+    double sn[T], cs[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) fast_sincos(al[t], sn[t], cs[t]);
 #pragma unroll 1
     for (int k = c.n - 1; k >= 1; --k) {          // the last sample (k = 0) does not update the state
-        double sn[T], cs[T];
-        if (k == c.n - 1) fast_sincos(al[0], sn[0], cs[0]);
-        else { sn[0] = 0.0; cs[0] = 1.0; }
-#pragma unroll
-        for (int t = 1; t < T; ++t) fast_sincos(al[t], sn[t], cs[t]);
         bool in_k[S], in_c[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -1148,10 +1148,27 @@ CTR_HD void sweep_tangent(const KRobot& rb, const Ctl<L>& c, double* base, doubl
         }
         // angles with the previous sample's torsion
         const double z0 = uz[0];
-        al[0] = 0.0;
+        al[0] = 0.0; sn[0] = 0.0; cs[0] = 1.0;
 #pragma unroll
         for (int t = 1; t < T; ++t) {
-            al[t] = x_fma(c.h, uz[t] - z0, al[t]);
+            const double d = c.h * (uz[t] - z0);
+            al[t] = al[t] + d;
+            if ((hi_word(d) & 0x7fffffff) < 0x3fb00000) {          // |d| < 2^-4: rotate (as FastSweep::step)
+                const double d2 = d * d;
+                double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
+                double ps = x_fma(CTRK_FC.qb4[0], d2, CTRK_FC.qb4[1]);
+                pc = x_fma(pc, d2, CTRK_FC.qa4[2]);
+                ps = x_fma(ps, d2, CTRK_FC.qb4[2]);
+                pc = x_fma(pc, d2, CTRK_FC.qa4[3]);
+                ps = x_fma(ps, d2, CTRK_FC.qb4[3]);
+                const double cd = x_fma(pc, d2, 1.0);
+                const double sd = x_fma(d * d2, ps, d);
+                const double s1 = x_fma(cs[t], sd, sn[t] * cd);
+                const double c1 = x_fma(-sn[t], sd, cs[t] * cd);
+                sn[t] = s1; cs[t] = c1;
+            } else {
+                fast_sincos(al[t], sn[t], cs[t]);
+            }
 #pragma unroll
             for (int j = 0; j < U; ++j) dal[t][j] = x_fma(c.h, duz[t][j] - duz[0][j], dal[t][j]);
         }
