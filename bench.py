@@ -100,6 +100,11 @@ class ClockSampler:
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
 
+    def mark(self):
+        """Start of the timed region: forget what was sampled before (the thread is started during
+        warm-up because the first NVML queries of a process take tens of milliseconds)."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         if self._t:
             self._stop.set()
@@ -275,13 +280,14 @@ def main():
         peak_tflops = max(peak_tflops, flops / (ev0.elapsed_time(ev1) * 1e-3) / 1e12)
 
     # ---- warm-up, then the timed region ----------------------------------------------------------
+    clocks = ClockSampler(visible_index(local))
+    clocks.start()
     for i in range(max(a.warmup, 3)):
         one_step(i)
     barrier()
-    clocks = ClockSampler(visible_index(local))
     launches0 = ctrfk.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
-    clocks.start()
+    clocks.mark()
     evs[0].record()
     for i in range(a.steps):
         one_step(i)

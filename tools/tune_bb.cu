@@ -1,7 +1,9 @@
 // tune_bb.cu — standalone tuning harness (not part of the product): times the AoS backbone kernels
 // of ctr_sec3_tub4 (layout 3,2,1,1) on 200 k configurations x 256 frames.
-//   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -DCTRK_CK_CTAS=10 -DCTRK_CK_WARPS=2 \
-//        tools/tune_bb.cu -o tools/tune_bb_10_2
+//   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -DCTRK_CK_CTAS=6 -DCTRK_CK_WARPS=2 \
+//        tools/tune_bb.cu -o tools/tune_bb_6_2 ; tools/tune_bb_6_2 1000000
+// -DCTRK_CK_CTAS=n        register cap of the emit kernel (resident CTAs per SM)
+// -DCTRK_BB_EXPERIMENT=1  pass 1 only;  =2  frames computed but not stored (DESIGN.md §4.3 timings)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
