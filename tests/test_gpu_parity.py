@@ -584,6 +584,55 @@ def test_single_configuration_with_odd_max_samples(ctrfk, oracle, robots, dev):
         eng.close()
 
 
+def test_concurrent_calls_on_one_handle(ctrfk, oracle, robots, engines):
+    """include/ctr_fk.h: a handle is immutable after create, any thread may call ctr_fk_batch on it
+    concurrently with distinct streams; ctr_fk_batch_host calls are serialised per handle.  Four
+    threads hammer one engine (fixed-N, step mode with binning temporaries, host path) and every
+    result must equal the one computed alone."""
+    import threading
+    name = "ctr_sec3_tub3.xml"
+    d, eng = robots[name], engines[name]
+    B = 20000
+    jobs = []
+    for w in range(4):
+        jv = ctrfk.sample_joints_host(d, 900 + w, 0, B)
+        mode, kw = ((1, dict(nsamples=200 + w)), (0, dict(step=d.max_length / (150.0 + w))))[w % 2]
+        jobs.append((jv, mode, kw, run_gpu(ctrfk, eng, jv, mode, **kw)))
+    errors = []
+
+    def worker(w):
+        try:
+            jv_np, mode, kw, ref = jobs[w]
+            stream = torch.cuda.Stream()
+            jv = torch.from_numpy(jv_np).cuda()
+            tip = torch.empty((B, 12), dtype=torch.float64, device="cuda")
+            n = torch.empty((B,), dtype=torch.int32, device="cuda")
+            host_tip = np.empty((B, 12))
+            torch.cuda.synchronize()
+            for it in range(25):
+                tip.fill_(-1.0)
+                stream.wait_stream(torch.cuda.current_stream())
+                eng.batch(jv, B, mode, tip=tip, n_out=n, stream=stream.cuda_stream, **kw)
+                stream.synchronize()
+                if not (np.array_equal(tip.cpu().numpy(), ref["tip"]) and np.array_equal(n.cpu().numpy(), ref["n"])):
+                    errors.append("thread %d iteration %d: device-pointer result differs" % (w, it))
+                    return
+                if it % 5 == 0:
+                    eng.batch_host(jv_np, B, mode, tip=host_tip, **kw)
+                    if not np.array_equal(host_tip, ref["tip"]):
+                        errors.append("thread %d iteration %d: host-pointer result differs" % (w, it))
+                        return
+        except Exception as e:          # noqa: BLE001 - report from the worker
+            errors.append("thread %d: %r" % (w, e))
+
+    ts = [threading.Thread(target=worker, args=(w,)) for w in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 def test_alignment_and_odd_sizes(ctrfk, oracle, robots, engines):
     """Odd joint counts and odd batch sizes through the host-pointer paths (staging sub-buffers
     must stay 16-byte aligned) and rejection of misaligned device views."""
