@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--max-samples", type=int, default=256, help="MaxSamples of the robot (install.sh:96 uses 256)")
     ap.add_argument("--strict", action="store_true", help="STRICT arithmetic kernels")
     ap.add_argument("--backbone", action="store_true", help="full backbone + radius output (config 4)")
+    ap.add_argument("--soa", action="store_true", help="with --backbone: [MaxS][12][B] output layout (CTR_FK_FLAG_SOA)")
     ap.add_argument("--f32", action="store_true", help="FP32 state arithmetic variant")
     ap.add_argument("--shoot", action="store_true", help="base-angle shooting solve (ctr_fk_batch_base) instead of FK")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
@@ -58,7 +59,7 @@ def workload_name(a):
         a.robot, "{:,}".format(a.batch).replace(",", "_"),
         ("fixed N=%d samples (calcKinematic(JV, NSamples))" % a.nsamples) if a.mode == "F"
         else "step = MaxLength/%d (calcKinematic(JV, ArcLengthStep))" % a.nsamples,
-        "backbone+radius" if a.backbone else "tip pose")
+        ("backbone+radius" + (" (SoA layout)" if getattr(a, "soa", False) else "")) if a.backbone else "tip pose")
 
 
 class ClockSampler:
@@ -217,6 +218,8 @@ def main():
     mode = ctrfk.MODE_NSAMPLE if a.mode == "F" else ctrfk.MODE_STEP
     step_len = desc.max_length / a.nsamples
     flags = ctrfk.FLAG_STRICT if a.strict else 0
+    if a.backbone and a.soa:
+        flags |= ctrfk.FLAG_SOA
     stream = torch.cuda.current_stream().cuda_stream
 
     # two input/output sets, alternated, so consecutive steps never touch the same lines
@@ -317,7 +320,7 @@ def main():
     prof_json = os.path.join(REPO, "profiles", "dram_traffic.json")
     if os.path.exists(prof_json):
         try:
-            ent = json.load(open(prof_json)).get(("backbone" if a.backbone else "tip") + "_" + a.mode)
+            ent = json.load(open(prof_json)).get((("backbone_soa" if a.soa else "backbone") if a.backbone else "tip") + "_" + a.mode)
             if ent and ent["robot"] == a.robot and ent["batch"] == B and not (a.strict or a.f32 or a.shoot):
                 traffic = ent["bytes"]
         except Exception:

@@ -57,7 +57,8 @@ extern "C" {
 /* flags for ctr_fk_batch* */
 #define CTR_FK_FLAG_STRICT     1u  /* reference operation order, libm-grade sin/cos/div/sqrt   */
 #define CTR_FK_FLAG_NO_BINNING 2u  /* step mode: do not sort configurations by sample count    */
-#define CTR_FK_FLAG_SOA        4u  /* backbone laid out [k][12][B] instead of [B][MaxS][12]     */
+#define CTR_FK_FLAG_SOA        4u  /* backbone laid out [k][12][B] instead of [B][MaxS][12]:
+                                       the fastest backbone path (coalesced stores, no scratch)  */
 
 /* error codes (<0) */
 #define CTR_FK_E_NULL      -1   /* null handle / required pointer                               */

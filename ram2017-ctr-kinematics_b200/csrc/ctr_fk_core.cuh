@@ -651,6 +651,11 @@ CTR_HD void se3_step_fast(double ux, double uy, double uz, double h, double ztol
 #ifdef CTRK_COUNT_COLD
 static long long g_iter_total = 0, g_iter_cold = 0, g_iter_cold_delta = 0;
 #endif
+// C++14 stand-in for `if constexpr`: only functors used with EMIT need emit_hot/emit_generic
+template <bool EMIT, bool HOT> struct EmitPending { template <class F> static CTR_HD void call(F&) {} };
+template <> struct EmitPending<true, true>  { template <class F> static CTR_HD void call(F& f) { f.emit_hot(); } };
+template <> struct EmitPending<true, false> { template <class F> static CTR_HD void call(F& f) { f.emit_generic(); } };
+
 struct NoHook {            // run_hooked(): called before sample k (k = N-2 .. 0) is processed
     template <class SW> CTR_HD void operator()(int, const SW&) const {}
 };
@@ -791,7 +796,9 @@ struct FastSweep {
     // tail_rt: run-time form of TAIL for resumed partial sweeps (run_range): sample 0 reports the
     // angle before the update, like the reference's last iteration (robot_i.h:1203-1238); the
     // state update itself is then dead and harmless.
-    template <bool HEAD, bool TAIL, bool HOT, bool ROT = false>
+    // EMIT (run_emit): the on_sample functor keeps the previous sample pending and turns it into
+    // a frame here, next to this sample's arithmetic, exactly like (A) does for the tip.
+    template <bool HEAD, bool TAIL, bool HOT, bool ROT = false, bool EMIT = false>
     CTR_HD void step(int k, const double* dl, double sxy_p, double m_p, bool tail_rt = false)
     {
         // ---- (A) accumulate the pending sample k+1 (independent of everything below) -----------
@@ -799,6 +806,7 @@ struct FastSweep {
             if (HOT) accumulate_hot(pux, puy, puz, sxy_p, m_p);
             else     accumulate_generic(pux, puy, puz);
         }
+        EmitPending<EMIT && !HEAD, HOT>::call(on_sample);
         // ---- (B) this sample ---------------------------------------------------------------------
         double s0 = 0.0, c0 = 1.0;                      // tube 0 is pinned to 0 after the head step
         if (HEAD) fast_sincos(al[0], s0, c0);
@@ -928,6 +936,48 @@ struct FastSweep {
             else if (amax < 0x408f0000 && dmax < 0x40300000) step<false, false, true, false>(k, dl, 0.0, 0.0, tail);
             else                                            step<false, false, false>(k, dl, 0.0, 0.0, tail);
         }
+    }
+
+    // Full sweep for a functor that emits frames one sample late (PendingFrameEmitter; thread-per-
+    // configuration backbone kernel): as run(), with the frame of sample k+1 built inside
+    // iteration k.  An iteration is hot when both the sweep and the pending frame qualify for
+    // their branch-free forms.
+    CTR_HD void run_emit()
+    {
+        static_assert(!WANT_TIP, "the frame product is the functor's");
+        const int n = c.n;
+        double dl[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) dl[t] = 0.0;
+        if (n == 1) {
+            step<true, true, false>(0, dl, 0.0, 0.0);
+        } else {
+            step<true, false, false>(n - 1, dl, 0.0, 0.0);
+#pragma unroll 1
+            for (int k = n - 2; k >= 1; --k) {
+                int dmax = 0, amax = 0;
+                const double z0 = uzs[0];
+#pragma unroll
+                for (int t = 1; t < T; ++t) {
+                    dl[t] = c.h * (uzs[t] - z0);
+                    const int d = hi_word(dl[t]) & 0x7fffffff;
+                    const int a = hi_word(al[t]) & 0x7fffffff;
+                    dmax = d > dmax ? d : dmax;
+                    amax = a > amax ? a : amax;
+                }
+                const bool eh = on_sample.pending_hot();
+                if (eh && dmax < 0x3fb00000)                           step<false, false, true, true, true>(k, dl, 0.0, 0.0);
+                else if (eh && amax < 0x408f0000 && dmax < 0x40300000) step<false, false, true, false, true>(k, dl, 0.0, 0.0);
+                else                                                   step<false, false, false, false, true>(k, dl, 0.0, 0.0);
+            }
+            {
+                const double z0 = uzs[0];
+#pragma unroll
+                for (int t = 1; t < T; ++t) dl[t] = c.h * (uzs[t] - z0);    // unused by the tail
+            }
+            step<false, true, false, false, true>(0, dl, 0.0, 0.0);
+        }
+        on_sample.emit_generic();          // sample 0
     }
 
     template <class Hook>
@@ -1436,6 +1486,68 @@ CTR_HD void emit_run(const KRobot& rb, const Ctl<L>& c, const SegPlan& p, int la
     sw.resume(rec);
     sw.run_range(kh, k0);
 }
+
+// on_sample functor for a FULL sweep (FastSweep::run_emit): operator() only records the sample;
+// the frame is built one iteration later by emit_hot()/emit_generic(), called from
+// FastSweep::step next to the following sample's arithmetic, so the two dependency chains overlap.
+// I starts as the total product T = E_0 ... E_ktip (a first sweep with WANT_TIP); emitting sample k
+// stores Frame_k = Init Rz(alpha_k + theta) I and leaves I = I inv(E_k) = I_{k-1}.  Samples above
+// ktip (the dropped tip sample of step mode) are skipped.
+template <class StoreFrame>
+struct PendingFrameEmitter {
+    const KRobot* rb;
+    StepConsts    kc;
+    double        theta;
+    StoreFrame    store;
+    QT            I;
+    int           ktip;
+    int           pk;                    // pending sample, -1: none
+    double        pux, puy, puz, pal;
+    double        psxy, pm;              // |u_xy|^2 and (h|u|/2)^2 of the pending sample (pending_hot)
+
+    CTR_HD void operator()(int k, double ux, double uy, double uz, double al)
+    {
+        pk = (k <= ktip) ? k : -1;
+        pux = ux; puy = uy; puz = uz; pal = al;
+    }
+    // branch-free forms apply: series SE(3) step of the first tier, bounded frame angle
+    CTR_HD bool pending_hot()
+    {
+        psxy = x_fma(puy, puy, pux * pux);
+        const double n2 = x_fma(puz, puz, psxy);
+        pm = n2 * kc.hh2;
+        return pk >= 0 && le_nonneg(kc.ztol2, n2) && hi_word(pm) < 0x3f700000 &&
+               (hi_word(pal + theta) & 0x7fffffff) < 0x40900000;
+    }
+    CTR_HD void emit_hot()               // after pending_hot() returned true
+    {
+        double shf, chf, F[12];
+        sincos_bounded(0.5 * (pal + theta), shf, chf);
+        qt_frame(*rb, I, shf, chf, F);
+        store(pk, F);
+        double qa, qb, qc;
+        se3_series4(pm, qa, qb, qc);
+        const double b2 = kc.h * qb, b = kc.hh * qb;
+        QT E;
+        E.w = qa; E.x = b * pux; E.y = b * puy; E.z = b * puz;
+        const double C = kc.h3 * qc, cz = C * puz;
+        E.px = x_fma(cz, pux, b2 * E.y);
+        E.py = x_fma(cz, puy, -(b2 * E.x));
+        E.pz = x_fma(-C, psxy, kc.h);
+        I = qt_mul_inv(I, E);
+    }
+    CTR_HD void emit_generic()
+    {
+        if (pk < 0) return;
+        double shf, chf, F[12];
+        fast_sincos(0.5 * (pal + theta), shf, chf);
+        qt_frame(*rb, I, shf, chf, F);
+        store(pk, F);
+        QT E;
+        se3_step_fast_k(pux, puy, puz, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
+        I = qt_mul_inv(I, E);
+    }
+};
 
 // robot_i.h:1286-1307: outer radius of the section covering each sample.  Writes radius[0..n)
 // with stride `stride` doubles.

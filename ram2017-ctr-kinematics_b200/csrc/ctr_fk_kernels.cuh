@@ -601,6 +601,64 @@ fk_backbone_emit_kernel(const __grid_constant__ KRobot rb, const __grid_constant
     }
 }
 
+// ---- backbone kernel, SoA layout [MaxS][12][B], FAST arithmetic ---------------------------------
+// With configurations along the fastest axis a thread-per-configuration kernel already writes
+// coalesced (a warp stores 32 x 8 B contiguous per matrix entry), so nothing needs to be parked or
+// handed to other lanes: the thread sweeps twice.  Sweep 1 is the tip solver (total product T);
+// sweep 2 repeats the sweep from the tip and emits Frame_k = Init Rz(alpha_k+theta) I_k with
+// I_{ktip} = T and I_{k-1} = I_k inv(E_k), one sample late so the frame arithmetic overlaps the
+// next sweep step (FastSweep::run_emit).  No shared memory, no scratch traffic at all: DRAM sees
+// the joint values and the output.
+struct FrameStoreSoa {
+    double* base;            // backbone + cfg
+    int64_t B;
+    double* tip;             // nullable
+    int     ktip;
+    __device__ __forceinline__ void operator()(int k, const double* F) const
+    {
+        double* p = base + (int64_t)k * 12 * B;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) p[j * B] = F[j];
+        if (k == ktip && tip) store_tf(tip, F);
+    }
+};
+
+template <class L>
+__global__ void __launch_bounds__(kBlock, 4)
+fk_backbone_soa_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= a.B) return;
+    const int64_t cfg = a.order ? (int64_t)a.order[i] : i;
+    double q[L::NJ];
+    load_jv<L>(a.jv, cfg, q);
+    Ctl<L> c;
+    setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
+    if (c.status) { write_invalid<L>(a, cfg); return; }
+
+    QT T;
+    {
+        FastSweep<L, true, NoSample> s1(rb, c, NoSample{});
+        s1.run();
+        T.w = s1.Qw; T.x = s1.Qx; T.y = s1.Qy; T.z = s1.Qz; T.px = s1.Px; T.py = s1.Py; T.pz = s1.Pz;
+        if (a.alpha_base) {
+#pragma unroll
+            for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = s1.al[t];
+        }
+    }
+    {
+        const FrameStoreSoa fs{a.backbone + cfg, a.B, a.tip ? a.tip + cfg * 12 : nullptr, c.nframes - 1};
+        const PendingFrameEmitter<FrameStoreSoa> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
+                                                    -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        FastSweep<L, false, PendingFrameEmitter<FrameStoreSoa>> s2(rb, c, em);
+        s2.run_emit();
+    }
+    if (a.radius) fill_radius<L>(rb, c, a.radius + cfg, a.B);
+    if (a.n_out) a.n_out[cfg] = c.nframes;
+    if (a.step_out) a.step_out[cfg] = c.h;
+    if (a.status) a.status[cfg] = 0;
+}
+
 #define CTRK_LAUNCH_CASE(KERNEL, FASTV, S, A, Bq, C)                                              \
     case S * 1000 + A * 100 + Bq * 10 + C:                                                        \
         KERNEL<Lay<S, A, Bq, C>, FASTV><<<grid, kBlock, 0, st>>>(rb, a);                          \

@@ -60,6 +60,19 @@ cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cud
         count_launch();
         return cudaGetLastError();
     }
+    if (a.soa) {        // two sweeps per thread, frames emitted coalesced across configurations
+        switch (key) {
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: \
+        fk_backbone_soa_kernel<Lay<S, A, Bq, C>><<<grid, kBlock, 0, st>>>(rb, a); \
+        break;
+            CTRK_FOR_EACH_LAYOUT_K(X)
+#undef X
+            default: return cudaErrorInvalidValue;
+        }
+        count_launch();
+        return cudaGetLastError();
+    }
     switch (key) {
 #define X(S, A, Bq, C) CTRK_LAUNCH_CASE(fk_backbone_kernel, true, S, A, Bq, C)
         CTRK_FOR_EACH_LAYOUT_K(X)

@@ -269,3 +269,41 @@ extern "C" int hostsim_emit(const ctr_robot_desc* d, const double* jv, int64_t B
     }
     return 0;
 }
+
+// Thread-per-configuration frame emission (the SoA backbone kernel's scheme): a first sweep for the
+// total product, a second sweep emitting frames one sample late (FastSweep::run_emit).
+namespace {
+template <class L>
+void emit_full_all(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, double* frames)
+{
+    for (int64_t i = 0; i < B; ++i) {
+        Ctl<L> c;
+        setup_control<L>(rb, jv + i * L::NJ, mode, step, ns, c);
+        if (c.status) continue;
+        FastSweep<L, true, NoSample> s1(rb, c, NoSample{});
+        s1.run();
+        QT T;
+        T.w = s1.Qw; T.x = s1.Qx; T.y = s1.Qy; T.z = s1.Qz; T.px = s1.Px; T.py = s1.Py; T.pz = s1.Pz;
+        FrameStoreHost fs{frames + i * 12 * (int64_t)rb.maxs};
+        PendingFrameEmitter<FrameStoreHost> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
+                                               -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        FastSweep<L, false, PendingFrameEmitter<FrameStoreHost>> s2(rb, c, em);
+        s2.run_emit();
+    }
+}
+}  // namespace
+
+extern "C" int hostsim_emit_full(const ctr_robot_desc* d, const double* jv, int64_t B, int mode, double step, int ns,
+                                 double* frames)
+{
+    KRobot rb;
+    int rc = make_krobot(d, &rb);
+    if (rc) return rc;
+    switch (layout_key(d)) {
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: emit_full_all<Lay<S, A, Bq, C>>(rb, jv, B, mode, step, ns, frames); break;
+        CTRK_FOR_EACH_LAYOUT(X)
+#undef X
+        default: return CTR_FK_E_DESC;
+    }
+    return 0;
+}

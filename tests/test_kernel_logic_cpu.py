@@ -227,20 +227,23 @@ def test_frame_emission_from_checkpoints_matches_oracle(ctrfk, oracle, hostsim, 
     d = robots[name]
     jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name] + 5, 0, 300), util.edge_joint_sets(d)])
     B = jv.shape[0]
-    hostsim.hostsim_emit.restype = C.c_int
-    hostsim.hostsim_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    for fn in (hostsim.hostsim_emit, hostsim.hostsim_emit_full):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
     for mode, step, ns in ((ctrfk.MODE_NSAMPLE, 0.0, 256), (ctrfk.MODE_STEP, d.max_length / 256.0, 0),
                            (ctrfk.MODE_NSAMPLE, 0.0, 1), (ctrfk.MODE_NSAMPLE, 0.0, 2), (ctrfk.MODE_NSAMPLE, 0.0, 31),
                            (ctrfk.MODE_NSAMPLE, 0.0, 33), (ctrfk.MODE_NSAMPLE, 0.0, 64), (ctrfk.MODE_NSAMPLE, 0.0, 65),
                            (ctrfk.MODE_NSAMPLE, 0.0, 225), (ctrfk.MODE_STEP, 0.004, 0), (ctrfk.MODE_STEP, 0.03, 0)):
         o = oracle.fk_batch(d, jv, mode, step=step, nsamples=ns, backbone=True)
-        got = np.full((B, d.max_samples, 12), np.nan)
-        assert hostsim.hostsim_emit(C.addressof(d), jv.ctypes.data, B, mode, step, ns, got.ctypes.data) == 0
-        worst_p = worst_r = 0.0
-        for i in range(B):
-            nf = int(o["n"][i])
-            assert np.isfinite(got[i, :nf]).all(), (mode, step, ns, i)
-            assert np.isnan(got[i, nf:]).all(), (mode, step, ns, i)       # nothing beyond the last frame
-            dp, ang = util.pose_errors(o["backbone"][i, :nf], got[i, :nf])
-            worst_p = max(worst_p, dp.max()); worst_r = max(worst_r, ang.max())
-        assert worst_p < 2e-10 and worst_r < 1e-11, (mode, step, ns, worst_p, worst_r)
+        # per-run emission from saved records (AoS kernel) and full second sweep (SoA kernel)
+        for fn in (hostsim.hostsim_emit, hostsim.hostsim_emit_full):
+            got = np.full((B, d.max_samples, 12), np.nan)
+            assert fn(C.addressof(d), jv.ctypes.data, B, mode, step, ns, got.ctypes.data) == 0
+            worst_p = worst_r = 0.0
+            for i in range(B):
+                nf = int(o["n"][i])
+                assert np.isfinite(got[i, :nf]).all(), (mode, step, ns, i)
+                assert np.isnan(got[i, nf:]).all(), (mode, step, ns, i)       # nothing beyond the last frame
+                dp, ang = util.pose_errors(o["backbone"][i, :nf], got[i, :nf])
+                worst_p = max(worst_p, dp.max()); worst_r = max(worst_r, ang.max())
+            assert worst_p < 2e-10 and worst_r < 1e-11, (mode, step, ns, worst_p, worst_r)
