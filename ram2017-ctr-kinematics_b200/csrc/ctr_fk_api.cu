@@ -36,7 +36,7 @@ namespace {
 
 // configurations below this count are not worth three extra launches for binning
 constexpr int64_t kMinBinBatch = 8192;
-// the binning kernels keep 2 x (MaxSamples + 2) counters in shared memory
+// the binning kernel keeps 2 x (MaxSamples + 2) counters in shared memory
 constexpr int kMaxBinSamples = 4096;
 // host-pointer path: configurations per pipelined chunk
 constexpr int64_t kHostChunk = 65536;   // 6.3 MB out per chunk: PCIe-bound, short pipeline fill/drain
@@ -92,24 +92,15 @@ int check_common(ctr_fk_handle h, const double* jv, int64_t B, int mode, double 
     return 0;
 }
 
-// Build `order` (longest sweeps first) for a step-mode batch.  Stream-ordered allocations only.
+// Build `order` (longest sweeps first inside every window of 16384 configurations) for a step-mode
+// batch.  One stream-ordered allocation, freed by the caller after the solver launch.
 cudaError_t make_order(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t ns,
                        int32_t** order_out, cudaStream_t st)
 {
-    const int nbins = h->rb.maxs + 2;
-    int32_t*  n = nullptr;
-    int32_t*  order = nullptr;
-    uint32_t* hist = nullptr;
-    cudaError_t e;
-    if ((e = cudaMallocAsync((void**)&n, sizeof(int32_t) * (size_t)B, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync((void**)&order, sizeof(int32_t) * (size_t)B, st)) != cudaSuccess) { cudaFreeAsync(n, st); return e; }
-    if ((e = cudaMallocAsync((void**)&hist, sizeof(uint32_t) * (size_t)nbins, st)) != cudaSuccess) { cudaFreeAsync(n, st); cudaFreeAsync(order, st); return e; }
-    e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)nbins, st);
-    if (e == cudaSuccess) e = launch_count_samples(h->key, h->rb, jv, B, mode, step, ns, n, hist, st);
-    if (e == cudaSuccess) e = launch_bin_offsets(hist, nbins, st);
-    if (e == cudaSuccess) e = launch_bin_scatter(n, B, hist, order, nbins, st);
-    cudaFreeAsync(n, st);
-    cudaFreeAsync(hist, st);
+    int32_t* order = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&order, sizeof(int32_t) * (size_t)B, st);
+    if (e != cudaSuccess) return e;
+    e = launch_bin_local(h->key, h->rb, jv, B, mode, step, ns, order, st);
     if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
     *order_out = order;
     return cudaSuccess;

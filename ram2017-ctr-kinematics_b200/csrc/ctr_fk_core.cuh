@@ -656,16 +656,10 @@ template <bool EMIT, bool HOT> struct EmitPending { template <class F> static CT
 template <> struct EmitPending<true, true>  { template <class F> static CTR_HD void call(F& f) { f.emit_hot(); } };
 template <> struct EmitPending<true, false> { template <class F> static CTR_HD void call(F& f) { f.emit_generic(); } };
 
-struct NoHook {            // run_hooked(): called before sample k (k = N-2 .. 0) is processed
-    template <class SW> CTR_HD void operator()(int, const SW&) const {}
-};
-struct ResumeTag {};       // FastSweep constructor that leaves the state to resume()
-
 template <class L, bool WANT_TIP, class OnSample>
 struct FastSweep {
     static constexpr int  S = L::S, T = L::T;
-    // state a sweep can be resumed from: alpha_1..alpha_{T-1}, z_0..z_{T-1}, arc position
-    static constexpr int  kStateDoubles = 2 * T;
+
     static constexpr bool want_tip = WANT_TIP;   // compile-time: keeps the accumulation of the
                                                  // pending sample in the same basic block as the
                                                  // arithmetic of the current one
@@ -695,37 +689,6 @@ struct FastSweep {
         a_tip = 0.0;
         pos = c.arc_end;
     }
-    CTR_HD FastSweep(const KRobot& rb_, const Ctl<L>& c_, const OnSample& os, ResumeTag)
-        : rb(rb_), c(c_), on_sample(os)
-    {
-        kc = make_step_consts(c.h, rb.ztol);
-#pragma unroll
-        for (int t = 0; t + 1 < T; ++t) hko[t] = c.h * rb.onu[t] * rb.kappa[L::sec_of(t)];
-        Qw = 1.0; Qx = Qy = Qz = 0.0; Px = Py = Pz = 0.0;
-        pux = puy = puz = 0.0;
-        a_tip = 0.0;
-    }
-    // State before sample k (k <= N-2) is processed, as run_hooked() presents it to its hook.
-    CTR_HD void save_state(double* v) const
-    {
-#pragma unroll
-        for (int t = 1; t < T; ++t) v[t - 1] = al[t];
-#pragma unroll
-        for (int t = 0; t < T; ++t) v[T - 1 + t] = uzs[t];
-        v[2 * T - 1] = pos;
-    }
-    // Counterpart: continue a sweep from a saved state.  sin/cos of the tube angles are evaluated
-    // afresh (the original sweep carried them by rotation; both are accurate to a few ulp).
-    CTR_HD void resume(const double* v)
-    {
-        al[0] = 0.0; sn[0] = 0.0; cs[0] = 1.0;
-#pragma unroll
-        for (int t = 1; t < T; ++t) { al[t] = v[t - 1]; fast_sincos(al[t], sn[t], cs[t]); }
-#pragma unroll
-        for (int t = 0; t < T; ++t) uzs[t] = v[T - 1 + t];
-        pos = v[2 * T - 1];
-    }
-
     // (Q,P) <- E (Q,P) for one step given as unit quaternion e and translation pe
     static CTR_HD void compose(double ew, double ex, double ey, double ez, double pex, double pey, double pez,
                                double& Qw, double& Qx, double& Qy, double& Qz, double& Px, double& Py, double& Pz)
@@ -750,15 +713,6 @@ struct FastSweep {
     CTR_HD void apply(double ew, double ex, double ey, double ez, double pex, double pey, double pez)
     {
         compose(ew, ex, ey, ez, pex, pey, pez, Qw, Qx, Qy, Qz, Px, Py, Pz);
-    }
-    // Suffix product including the pending sample, E_{k+1} ... E_tip when called from a
-    // run_hooked() hook before sample k: qp = (w, x, y, z, px, py, pz).  Does not change the sweep.
-    CTR_HD void suffix_with_pending(double* qp) const
-    {
-        double ew, ex, ey, ez, pex, pey, pez;
-        se3_step_fast_k(pux, puy, puz, kc, ew, ex, ey, ez, pex, pey, pez);
-        qp[0] = Qw; qp[1] = Qx; qp[2] = Qy; qp[3] = Qz; qp[4] = Px; qp[5] = Py; qp[6] = Pz;
-        compose(ew, ex, ey, ez, pex, pey, pez, qp[0], qp[1], qp[2], qp[3], qp[4], qp[5], qp[6]);
     }
     CTR_HD void accumulate_generic(double ux, double uy, double uz)
     {
@@ -793,13 +747,10 @@ struct FastSweep {
     // (angle increments, valid when !TAIL), (sxy, m) describe the pending sample (valid when HOT).
     // ROT (with HOT): rotate the carried sin/cos by d_t; otherwise re-evaluate them from the new
     // angles with sincos_bounded (the caller has checked |alpha_t| < 1024).
-    // tail_rt: run-time form of TAIL for resumed partial sweeps (run_range): sample 0 reports the
-    // angle before the update, like the reference's last iteration (robot_i.h:1203-1238); the
-    // state update itself is then dead and harmless.
     // EMIT (run_emit): the on_sample functor keeps the previous sample pending and turns it into
     // a frame here, next to this sample's arithmetic, exactly like (A) does for the tip.
     template <bool HEAD, bool TAIL, bool HOT, bool ROT = false, bool EMIT = false>
-    CTR_HD void step(int k, const double* dl, double sxy_p, double m_p, bool tail_rt = false)
+    CTR_HD void step(int k, const double* dl, double sxy_p, double m_p)
     {
         // ---- (A) accumulate the pending sample k+1 (independent of everything below) -----------
         if (!HEAD && want_tip) {
@@ -855,7 +806,7 @@ struct FastSweep {
             al[0] = 0.0;
 #pragma unroll
             for (int t = 1; t < T; ++t) al[t] = al[t] + dl[t];
-            a_k = tail_rt ? a_k : al[T - 1];
+            a_k = al[T - 1];
             // torsion (section_i.h:243-286).  A section that does not reach this position yet
             // still has u_z = 0 (its update is masked by in_c, and in_c implies in_k), so the
             // in_k mask on the balance coefficients is redundant and dropped.
@@ -910,34 +861,6 @@ struct FastSweep {
         if (!TAIL) pos = x_sub(pos, c.h);
     }
 
-    CTR_HD void run() { NoHook nh; run_hooked(nh); }
-
-    // Samples kh .. k0 (kh <= N-2) of a sweep whose state was restored with resume().  Without the
-    // frame product every iteration qualifies for the hot forms as far as the step is concerned.
-    CTR_HD void run_range(int kh, int k0)
-    {
-        static_assert(!WANT_TIP, "partial sweeps do not carry the frame product");
-        double dl[T];
-        dl[0] = 0.0;
-#pragma unroll 1
-        for (int k = kh; k >= k0; --k) {
-            int dmax = 0, amax = 0;
-            const double z0 = uzs[0];
-#pragma unroll
-            for (int t = 1; t < T; ++t) {
-                dl[t] = c.h * (uzs[t] - z0);
-                const int d = hi_word(dl[t]) & 0x7fffffff;
-                const int a = hi_word(al[t]) & 0x7fffffff;
-                dmax = d > dmax ? d : dmax;
-                amax = a > amax ? a : amax;
-            }
-            const bool tail = (k == 0);
-            if (dmax < 0x3fb00000)                          step<false, false, true, true>(k, dl, 0.0, 0.0, tail);
-            else if (amax < 0x408f0000 && dmax < 0x40300000) step<false, false, true, false>(k, dl, 0.0, 0.0, tail);
-            else                                            step<false, false, false>(k, dl, 0.0, 0.0, tail);
-        }
-    }
-
     // Full sweep for a functor that emits frames one sample late (PendingFrameEmitter; thread-per-
     // configuration backbone kernel): as run(), with the frame of sample k+1 built inside
     // iteration k.  An iteration is hot when both the sweep and the pending frame qualify for
@@ -980,8 +903,7 @@ struct FastSweep {
         on_sample.emit_generic();          // sample 0
     }
 
-    template <class Hook>
-    CTR_HD void run_hooked(Hook& hook)
+    CTR_HD void run()
     {
         const int n = c.n;
         double dl[T];
@@ -994,7 +916,6 @@ struct FastSweep {
         step<true, false, false>(n - 1, dl, 0.0, 0.0);
 #pragma unroll 1
         for (int k = n - 2; k >= 1; --k) {
-            hook(k, *this);
             // top-of-iteration quantities shared by the hot tests and the hot steps
             int dmax = 0, amax = 0;
             const double z0 = uzs[0];
@@ -1025,70 +946,11 @@ struct FastSweep {
 #pragma unroll
             for (int t = 1; t < T; ++t) dl[t] = c.h * (uzs[t] - z0);    // unused by the tail
         }
-        hook(0, *this);
         step<false, true, false>(0, dl, 0.0, 0.0);
     }
 };
 
-// ---- checkpointed sweep (backbone kernels) -----------------------------------------------------
-// Frames need the prefix products E_0 ... E_k, the sweep produces sample N-1 first.  Instead of
-// parking every sample, the sweeping thread saves its state at 32 points; afterwards 32 workers
-// (the lanes of a warp) each repeat the sweep over their own run of cnt = ceil(frames/32) samples.
-//   run l      frames [l cnt, min((l+1) cnt, frames))
-//   state l    the sweep state before the highest sample of run l that is not sample N-1
-//   sample N-1 (the head step, different code) is parked by the sweeping thread itself.
-struct SegPlan {
-    int cnt;        // samples per run
-    int top;        // run holding the last frame
-    int kh_top;     // highest sample the top run repeats (below its first sample: nothing to repeat)
-    CTR_HD SegPlan(int n, int nframes)
-    {
-        cnt    = (nframes + 31) >> 5;
-        if (cnt < 1) cnt = 1;
-        top    = nframes > 0 ? (nframes - 1) / cnt : 0;
-        kh_top = (nframes - 1 < n - 2) ? nframes - 1 : n - 2;
-    }
-};
-
-// Hook for FastSweep::run_hooked: store(slot, sweep) at the scheduled samples.
-template <class Store>
-struct CkptHook {
-    Store store;
-    int   cnt, next_k, next_slot;
-    CTR_HD CkptHook(const SegPlan& p, const Store& st) : store(st), cnt(p.cnt)
-    {
-        next_slot = p.top;
-        next_k    = p.kh_top;
-        if (next_k < p.top * p.cnt) { next_slot = p.top - 1; next_k = p.top * p.cnt - 1; }
-    }
-    template <class SW>
-    CTR_HD void operator()(int k, const SW& sw)
-    {
-        if (k == next_k) {
-            store(next_slot, sw);
-            --next_slot;
-            next_k = (next_slot + 1) * cnt - 1;
-        }
-    }
-};
-
-// Run `lane` of the plan: emits on_sample(k, ux, uy, uz, alpha_k) for its samples, highest first.
-// ck = state saved for this run, head = parked sample N-1 (read only by the run that holds it).
-template <class L, class OnSample>
-CTR_HD void resweep_run(const KRobot& rb, const Ctl<L>& c, const SegPlan& p, int lane, const double* ck,
-                        const double* head, const OnSample& w)
-{
-    const int k0 = lane * p.cnt;
-    if (k0 >= c.nframes) return;
-    int kh = (k0 + p.cnt < c.nframes ? k0 + p.cnt : c.nframes) - 1;
-    if (kh == c.n - 1) { w(kh, head[0], head[1], head[2], head[3]); kh = c.n - 2; }
-    if (kh < k0) return;
-    FastSweep<L, false, OnSample> sw(rb, c, w, ResumeTag{});
-    sw.resume(ck);
-    sw.run_range(kh, k0);
-}
-
-// WANT_TIP = false skips the frame product (backbone kernels build frames in their second pass).
+// WANT_TIP = false skips the frame product (sample-only sweeps: STRICT backbone kernel, stability).
 template <class L, bool WANT_TIP, class OnSample>
 CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* albase,
                        OnSample on_sample)
@@ -1408,85 +1270,10 @@ CTR_HD QT qt_mul_inv(const QT& a, const QT& b)
     return r;
 }
 
-// ---- frame emission from a checkpointed sweep (backbone kernels) -------------------------------
-// The sweeping thread carries the suffix products S_k = E_k ... E_tip (the tip solver's
-// accumulation) and saves, per run of SegPlan, the sweep state plus S_{kh+1}, kh = the run's
-// highest sample.  With the total T = S_0 known after the sweep, the frame product of sample kh is
-//     I_kh = E_0 ... E_kh = T inv(S_{kh+1}),
-// and walking the run downwards, I_{k-1} = I_k inv(E_k).  So a worker repeats the sweep over its
-// run and emits Frame_k = Init Rz(alpha_k + theta) I_k as the samples appear: no second walk, no
-// scan across workers, nothing parked per sample.
-// Saved record of a run: [ sweep state (2T) | S_{kh+1} as w,x,y,z,px,py,pz (7) ].
-template <class L>
-struct EmitLayout {
-    static constexpr int kState  = 2 * L::T;
-    static constexpr int kRecord = kState + 7;
-    static constexpr int kStride = (kRecord + 3) & ~3;       // whole 32-B sectors
-};
-
-// on_sample functor of the repeated sweep: emits the frame of sample k, then strips E_k from I
-template <class StoreFrame>
-struct FrameEmitter {
-    const KRobot* rb;
-    QT*           I;
-    StepConsts    kc;
-    double        theta;
-    StoreFrame    store;
-    CTR_HD void operator()(int k, double ux, double uy, double uz, double al) const
-    {
-        double shf, chf, F[12];
-        const double ang = al + theta;
-        if ((hi_word(ang) & 0x7fffffff) < 0x40900000) sincos_bounded(0.5 * ang, shf, chf);
-        else                                          fast_sincos(0.5 * ang, shf, chf);
-        qt_frame(*rb, *I, shf, chf, F);
-        store(k, F);
-        QT E;
-        const double sxy = x_fma(uy, uy, ux * ux);
-        const double n2  = x_fma(uz, uz, sxy);
-        const double m   = n2 * kc.hh2;
-        if (le_nonneg(kc.ztol2, n2) && hi_word(m) < 0x3f700000) {
-            double qa, qb, qc;
-            se3_series4(m, qa, qb, qc);
-            const double b2 = kc.h * qb, b = kc.hh * qb;
-            E.w = qa; E.x = b * ux; E.y = b * uy; E.z = b * uz;
-            const double C = kc.h3 * qc, cz = C * uz;
-            E.px = x_fma(cz, ux, b2 * E.y);
-            E.py = x_fma(cz, uy, -(b2 * E.x));
-            E.pz = x_fma(-C, sxy, kc.h);
-        } else {
-            se3_step_fast_k(ux, uy, uz, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
-        }
-        *I = qt_mul_inv(*I, E);
-    }
-};
-
-// Run `lane` of the plan.  rec = this run's saved record, head = parked sample N-1 (read only by
-// the run that holds it), T = total product.  store(k, F[12]) receives the frames, highest first.
-template <class L, class StoreFrame>
-CTR_HD void emit_run(const KRobot& rb, const Ctl<L>& c, const SegPlan& p, int lane, const double* rec,
-                     const double* head, const QT& T, const StoreFrame& store)
-{
-    const int k0 = lane * p.cnt;
-    if (k0 >= c.nframes) return;
-    int kh = (k0 + p.cnt < c.nframes ? k0 + p.cnt : c.nframes) - 1;
-    QT I;
-    FrameEmitter<StoreFrame> em{&rb, &I, make_step_consts(c.h, rb.ztol), c.theta, store};
-    if (kh == c.n - 1) {
-        I = T;                                       // the tip frame; em() leaves I_{N-2} behind
-        em(kh, head[0], head[1], head[2], head[3]);
-        kh = c.n - 2;
-        if (kh < k0) return;
-    } else {
-        QT S;
-        const double* q = rec + EmitLayout<L>::kState;
-        S.w = q[0]; S.x = q[1]; S.y = q[2]; S.z = q[3]; S.px = q[4]; S.py = q[5]; S.pz = q[6];
-        I = qt_mul_inv(T, S);
-    }
-    FastSweep<L, false, FrameEmitter<StoreFrame>> sw(rb, c, em, ResumeTag{});
-    sw.resume(rec);
-    sw.run_range(kh, k0);
-}
-
+// ---- frame emission during a repeated sweep (backbone kernels) ----------------------------------
+// A first sweep with WANT_TIP gives the total product T = E_0 ... E_ktip.  A second sweep from the
+// tip then has the frame product of every sample for the price of one inverse step:
+//     I_ktip = T,   I_{k-1} = I_k inv(E_k),   Frame_k = Init Rz(alpha_k + theta) I_k.
 // on_sample functor for a FULL sweep (FastSweep::run_emit): operator() only records the sample;
 // the frame is built one iteration later by emit_hot()/emit_generic(), called from
 // FastSweep::step next to the following sample's arithmetic, so the two dependency chains overlap.

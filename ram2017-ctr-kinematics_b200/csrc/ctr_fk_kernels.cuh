@@ -67,7 +67,16 @@ template <class L, bool FAST>
 __global__ void __launch_bounds__(kBlock, FAST ? 4 : 1)
 fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    int64_t i;
+    if (a.windows) {
+        // `order` is sorted inside windows of kBinWindow entries.  CTAs take the windows rank-major:
+        // first every window's 128 longest sweeps, then the next 128 ... so the kernel as a whole
+        // still runs longest-first and ends on the shortest sweeps (no tail of long stragglers).
+        const int64_t w = blockIdx.x % a.windows, r = blockIdx.x / a.windows;
+        i = w * kBinWindow + r * kBlock + threadIdx.x;
+    } else {
+        i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    }
     if (i >= a.B) return;
     const int64_t cfg = a.order ? (int64_t)a.order[i] : i;
 
@@ -168,50 +177,10 @@ fk_backbone_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Fk
     if (a.status) a.status[cfg] = 0;
 }
 
-// ---- backbone kernel, AoS layout, FAST arithmetic: warp-parallel second pass ---------------------
-// The thread-per-configuration second pass above stores each frame 24.5 KB away from its warp
-// neighbours' frames and reads the parked samples with one dependent load per step (ncu, round 1:
-// 12.9 GB of DRAM traffic for 5.3 GB of output, long-scoreboard stalls dominate).  Here:
-//   pass 1  one thread per configuration sweeps tip -> base and parks (u_x,u_y,u_z,alpha) of every
-//           sample COMPACTLY at the start of the configuration's own output region
-//           ([k][4] doubles = n*32 B contiguous, 32-B aligned full-sector stores);
-//   pass 2  each warp takes the CTA's configurations one at a time: the n*32 B block is copied to
-//           shared memory with cp.async (16 B per lane per request, all requests in flight at
-//           once, double-buffered so the next configuration's block streams in while this one is
-//           processed); lane l owns the contiguous samples [l*c, (l+1)*c), c = ceil(n/32).  The
-//           running product I_k = E_0 ... E_k is a prefix "sum" over SE(3) composition, computed
-//           as lane-local products + a warp scan (5 shuffle rounds) + a second lane-local walk that
-//           emits Frame_k = Init Rz(alpha_k+theta) I_k.  A warp writes one configuration's n*96 B
-//           contiguously.  Transforms travel as (unit quaternion, translation): 7 doubles per
-//           shuffle, 37 FP64 instructions per composition.
-// Shared memory: kBbWarps warps x 2 buffers x MaxSamples x 32 B (32 KB per CTA at MaxSamples=256).
-constexpr int kBbWarps = 2;
-constexpr int kBbBufs = 1;              // staging buffers per warp (2 = prefetch the next block)
-constexpr int kBbBlock = kBbWarps * 32;
-constexpr int kBbMaxSamples = 1024;     // larger robots use the thread-per-configuration kernel
-
-struct BbShared {
-    double  h, theta;
-    double  end[kMaxSec];
-    int64_t cfg;
-    int     nframes;
-    int     ok;
-};
-
-__device__ __forceinline__ QT qt_shfl_up(const QT& t, int off)
-{
-    QT r;
-    r.w = __shfl_up_sync(0xffffffffu, t.w, off);   r.x = __shfl_up_sync(0xffffffffu, t.x, off);
-    r.y = __shfl_up_sync(0xffffffffu, t.y, off);   r.z = __shfl_up_sync(0xffffffffu, t.z, off);
-    r.px = __shfl_up_sync(0xffffffffu, t.px, off); r.py = __shfl_up_sync(0xffffffffu, t.py, off);
-    r.pz = __shfl_up_sync(0xffffffffu, t.pz, off);
-    return r;
-}
-
-// One 256-bit store (sm_100: STG.E.ENL2.256): a full 32-B sector per request.  These kernels are
-// bound by the number of L2 write requests their scattered stores generate, not by bytes
-// (ncu: long-scoreboard stalls on registers still owned by in-flight 16-B stores), so every store
-// here carries a whole sector.  `p` must be 32-B aligned.
+// One 256-bit store (sm_100: STG.E.ENL2.256): a full 32-B sector per request.  Scattered stores are
+// bound by the number of L2 write requests they generate, not by bytes (ncu on the first backbone
+// kernels: long-scoreboard stalls on registers still owned by in-flight 16-B stores), so the frame
+// stores carry whole sectors.  `p` must be 32-B aligned.
 __device__ __forceinline__ void st256(double* p, double a, double b, double c, double d)
 {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
@@ -223,392 +192,21 @@ __device__ __forceinline__ void store_tf256(double* dst, const double* t)
     st256(dst + 8, t[8], t[9], t[10], t[11]);
 }
 
-// parks a sample as one 32-B store
-struct ParkCompact {
-    double* base;
-    __device__ __forceinline__ void operator()(int k, double ux, double uy, double uz, double al) const
-    {
-        st256(base + 4 * (int64_t)k, ux, uy, uz, al);
-    }
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <class L>
-__global__ void __launch_bounds__(kBbBlock, 8)
-fk_backbone_warp_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
-{
-    extern __shared__ __align__(16) double sh_park[];       // [kBbWarps][2][maxs*4]
-    __shared__ BbShared sh[kBbBlock];
-    const int64_t i = (int64_t)blockIdx.x * kBbBlock + threadIdx.x;
-    BbShared me;
-    me.ok = 0; me.nframes = 0; me.cfg = 0; me.h = 0.0; me.theta = 0.0;
-#pragma unroll
-    for (int s = 0; s < kMaxSec; ++s) me.end[s] = 0.0;
-
-    // ---- pass 1: one thread per configuration, tip -> base sweep, samples parked in place -----
-    if (i < a.B) {
-        const int64_t cfg = a.order ? (int64_t)a.order[i] : i;
-        double q[L::NJ];
-        load_jv<L>(a.jv, cfg, q);
-        Ctl<L> c;
-        setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-        if (c.status) {
-            write_invalid<L>(a, cfg);
-        } else {
-            ParkCompact park;
-            park.base = a.backbone + cfg * 12 * (int64_t)rb.maxs;
-            double alb[L::T];
-            solve_fast<L, false>(rb, c, nullptr, alb, park);
-            if (a.n_out) a.n_out[cfg] = c.nframes;
-            if (a.step_out) a.step_out[cfg] = c.h;
-            if (a.alpha_base) {
-#pragma unroll
-                for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = alb[t];
-            }
-            if (a.status) a.status[cfg] = 0;
-            me.ok = 1; me.nframes = c.nframes; me.cfg = cfg; me.h = c.h; me.theta = c.theta;
-#pragma unroll
-            for (int s = 0; s < L::S; ++s) me.end[s] = c.end[s];
-        }
-    }
-    sh[threadIdx.x] = me;
-    __syncthreads();        // parked samples (global) and sh[] are visible to the whole CTA
-
-    // ---- pass 2: one warp per configuration ---------------------------------------------------
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* buf0 = sh_park + (size_t)warp * kBbBufs * 4 * rb.maxs;
-    auto prefetch = [&](int j, int which) {
-        const BbShared& cf = sh[warp * 32 + j];
-        if (cf.ok) {
-            const char* src = reinterpret_cast<const char*>(a.backbone + cf.cfg * 12 * (int64_t)rb.maxs);
-            char* dst = reinterpret_cast<char*>(buf0 + (size_t)which * 4 * rb.maxs);
-            const int bytes = cf.nframes * 32;
-            for (int o = lane * 16; o < bytes; o += 32 * 16) cp_async16(dst + o, src + o);
-        }
-        cp_async_commit();
-    };
-    if (kBbBufs == 2) prefetch(0, 0);
-    for (int j = 0; j < 32; ++j) {
-        if (kBbBufs == 2) {
-            if (j + 1 < 32) prefetch(j + 1, (j + 1) & 1);  // stream the next block in meanwhile
-            else            cp_async_commit();
-            cp_async_wait<1>();                             // this configuration's block has landed
-        } else {
-            prefetch(j, 0);
-            cp_async_wait<0>();
-        }
-        __syncwarp();
-        const BbShared& cf = sh[warp * 32 + j];
-        if (cf.ok) {                                        // warp-uniform
-            const int n   = cf.nframes;
-            const int cnt = (n + 31) >> 5;
-            const int k0  = lane * cnt;
-            const int k1  = (k0 + cnt < n) ? k0 + cnt : n;
-            const double* pk = buf0 + (size_t)(kBbBufs == 2 ? (j & 1) : 0) * 4 * rb.maxs;
-            double* slot0 = a.backbone + cf.cfg * 12 * (int64_t)rb.maxs;
-            const StepConsts kc = make_step_consts(cf.h, rb.ztol);
-
-            QT T = qt_identity();
-            bool allhot = true;       // every sample of this lane takes the branch-free forms below
-            for (int k = k0; k < k1; ++k) {
-                const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
-                const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);
-                const double n2 = x_fma(v1.x, v1.x, x_fma(v0.y, v0.y, v0.x * v0.x));
-                allhot = allhot && le_nonneg(kc.ztol2, n2) && hi_word(n2 * kc.hh2) < 0x3f700000 &&
-                         (hi_word(v1.y + cf.theta) & 0x7fffffff) < 0x40900000;
-                QT E;
-                se3_step_fast_k(v0.x, v0.y, v1.x, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
-                T = qt_mul(T, E);
-            }
-            const bool hot_walk = __all_sync(0xffffffffu, allhot);
-            // inclusive scan over lanes: T_l <- T_0 * ... * T_l
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const QT o = qt_shfl_up(T, off);
-                if (lane >= off) T = qt_mul(o, T);
-            }
-            QT I = qt_shfl_up(T, 1);
-            if (lane == 0) I = qt_identity();
-            {   // renormalise the carried rotation (|q| drifts by ~n ulp)
-                const double inv = rsqrt(I.w * I.w + I.x * I.x + I.y * I.y + I.z * I.z);
-                I.w *= inv; I.x *= inv; I.y *= inv; I.z *= inv;
-            }
-            if (hot_walk) {
-                // branch-free body, two samples per trip: the step and the frame trigonometry of
-                // sample k+1 overlap the (serial) product and frame assembly of sample k
-#pragma unroll 2
-                for (int k = k0; k < k1; ++k) {
-                    const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
-                    const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);   // (u_z, alpha_k)
-                    const double sxy = x_fma(v0.y, v0.y, v0.x * v0.x);
-                    const double m   = x_fma(v1.x, v1.x, sxy) * kc.hh2;
-                    double qa, qb, qc;
-                    se3_series4(m, qa, qb, qc);
-                    const double b2 = kc.h * qb, b = kc.hh * qb;
-                    QT E;
-                    E.w = qa; E.x = b * v0.x; E.y = b * v0.y; E.z = b * v1.x;
-                    const double C = kc.h3 * qc, cz = C * v1.x;
-                    E.px = x_fma(cz, v0.x, b2 * E.y);
-                    E.py = x_fma(cz, v0.y, -(b2 * E.x));
-                    E.pz = x_fma(-C, sxy, kc.h);
-                    I = qt_mul(I, E);
-                    double shf, chf, F[12];
-                    sincos_bounded(0.5 * (v1.y + cf.theta), shf, chf);
-                    qt_frame(rb, I, shf, chf, F);
-                    store_tf256(slot0 + (int64_t)k * 12, F);
-                    if (k == n - 1 && a.tip) store_tf(a.tip + cf.cfg * 12, F);
-                }
-            } else {
-                for (int k = k0; k < k1; ++k) {
-                    const double2 v0 = *reinterpret_cast<const double2*>(pk + 4 * k);
-                    const double2 v1 = *reinterpret_cast<const double2*>(pk + 4 * k + 2);   // (u_z, alpha_k)
-                    QT E;
-                    se3_step_fast_k(v0.x, v0.y, v1.x, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
-                    I = qt_mul(I, E);
-                    double shf, chf, F[12];
-                    fast_sincos(0.5 * (v1.y + cf.theta), shf, chf);
-                    qt_frame(rb, I, shf, chf, F);
-                    store_tf256(slot0 + (int64_t)k * 12, F);
-                    if (k == n - 1 && a.tip) store_tf(a.tip + cf.cfg * 12, F);
-                }
-            }
-            if (a.radius) {
-                // robot_i.h:1286-1307, lanes striding over the samples of each section's run
-                double* rad = a.radius + cf.cfg * (int64_t)rb.maxs;
-                int    begin = 0;
-                double rsec  = 0.0;
-#pragma unroll
-                for (int s = 0; s < L::S; ++s) {
-                    if (begin >= n) continue;
-                    rsec = rb.rad[s];
-                    const double qd = x_div(cf.end[s], cf.h);
-                    int stop = (qd >= 0.0 && qd < (double)n) ? (int)qd : n;
-                    if (stop < begin) stop = begin;
-                    for (int k = begin + lane; k < stop; k += 32) rad[k] = rsec;
-                    begin = stop;
-                }
-                __syncwarp();
-                if (lane == 0 && n > 0) rad[n - 1] = rsec;
-            }
-        }
-        __syncwarp();       // everyone is done with this buffer before it is refilled
-    }
-}
-
-// ---- backbone kernel, AoS layout, FAST arithmetic: checkpointed sweep, frames emitted per run ----
-// fk_backbone_warp_kernel moves 32 B per sample out to the output region in pass 1 and back in
-// pass 2, then needs two walks over the samples and a warp scan to turn them into frames.  Here
-// (scheme: ctr_fk_core.cuh, "frame emission from a checkpointed sweep"):
-//   pass 1  one thread per configuration runs the tip solver's sweep (suffix products carried,
-//           software-pipelined) and saves 32 records — sweep state + suffix product, 128-160 B —
-//           at the start of the configuration's own output region; sample N-1 is parked whole;
-//   pass 2  each warp takes the CTA's configurations one at a time; lane l repeats the sweep over
-//           its run of ceil(n/32) samples from record l and emits Frame_k as sample k appears
-//           (I_k = T inv(S_{k+1}), then I_{k-1} = I_k inv(E_k)).  No shared-memory staging, no
-//           scan, no second walk; a warp still writes one configuration's n*96 B region by itself,
-//           which keeps DRAM pages open (thread-per-configuration stores do not).
-// Round trip per configuration: 33 records (4-5 KB) instead of 16 KB of parked samples at N = 256.
-constexpr int kCkMinSamples = 128;      // below this the records are no smaller than parked samples
-#ifndef CTRK_BB_EXPERIMENT
-#define CTRK_BB_EXPERIMENT 0
-#endif
-#ifndef CTRK_CK_CTAS
-#define CTRK_CK_CTAS 6      // resident CTAs per SM the kernel is compiled for: 168 registers, 12 warps/SM (2-3 % faster than 128 registers x 16 warps; tools/tune_bb.cu)
-#endif
-#ifndef CTRK_CK_WARPS
-#define CTRK_CK_WARPS 2
-#endif
-constexpr int kCkWarps = CTRK_CK_WARPS;
-constexpr int kCkBlock = kCkWarps * 32;
-
-struct EmShared {            // what pass 2 needs to know about a configuration
-    double  h, theta;
-    double  end[kMaxSec];
-    double  T[7];            // total product E_0 ... E_{frames-1}
-    int64_t cfg;
-    int     n, nframes;      // nframes = 0: nothing to do (invalid configuration or beyond the batch)
-    int     stop[kMaxSec];   // radius runs (robot_i.h:1286-1307): section s covers samples [stop[s-1], stop[s])
-};
-
-__device__ __forceinline__ void ld256cg(const double* p, double& a, double& b, double& c, double& d)
-{
-    asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
-}
-
-template <class L>
-struct RecStoreGlobal {      // CkptHook store: one record = EmitLayout<L>::kStride doubles
-    double* base;
-    template <class SW>
-    __device__ __forceinline__ void operator()(int slot, const SW& sw) const
-    {
-        constexpr int R = EmitLayout<L>::kStride;
-        double v[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j) v[j] = 0.0;
-        sw.save_state(v);
-        sw.suffix_with_pending(v + EmitLayout<L>::kState);
-        double* p = base + (int64_t)slot * R;
-#pragma unroll
-        for (int g = 0; g < R; g += 4) st256(p + g, v[g], v[g + 1], v[g + 2], v[g + 3]);
-    }
-};
-struct HeadParkGlobal {      // on_sample of pass 1: only sample N-1 (the head step) is parked
-    double* dst;
-    int     nm1;
-    __device__ __forceinline__ void operator()(int k, double ux, double uy, double uz, double al) const
-    {
-        if (k == nm1) st256(dst, ux, uy, uz, al);
-    }
-};
-struct FrameStoreGlobal {    // emit_run store: 3 full sectors per frame
-    double* slot0;
-    double* tip;             // nullable
-    int     ktip;
-    __device__ __forceinline__ void operator()(int k, const double* F) const
-    {
-#if CTRK_BB_EXPERIMENT == 2      /* timing experiment: frames computed, (almost) never stored */
-        if (F[0] == 123.456) store_tf256(slot0 + (int64_t)k * 12, F);
-#else
-        store_tf256(slot0 + (int64_t)k * 12, F);
-#endif
-        if (k == ktip && tip) store_tf(tip, F);
-    }
-};
-
-template <class L>
-__global__ void __launch_bounds__(kCkBlock, CTRK_CK_CTAS)
-fk_backbone_emit_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
-{
-    constexpr int R = EmitLayout<L>::kStride;    // record stride, doubles
-    __shared__ EmShared sh[kCkBlock];
-    const int64_t i = (int64_t)blockIdx.x * kCkBlock + threadIdx.x;
-    EmShared me;
-    me.n = 0; me.nframes = 0; me.cfg = 0; me.h = 0.0; me.theta = 0.0;
-#pragma unroll
-    for (int s = 0; s < kMaxSec; ++s) { me.end[s] = 0.0; me.stop[s] = 0; }
-#pragma unroll
-    for (int q = 0; q < 7; ++q) me.T[q] = 0.0;
-
-    // ---- pass 1: one thread per configuration, tip -> base sweep, 32 records saved --------------
-    if (i < a.B) {
-        const int64_t cfg = a.order ? (int64_t)a.order[i] : i;
-        double q[L::NJ];
-        load_jv<L>(a.jv, cfg, q);
-        Ctl<L> c;
-        setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-        if (c.status) {
-            write_invalid<L>(a, cfg);
-        } else {
-            double* slot0 = a.backbone + cfg * 12 * (int64_t)rb.maxs;
-            const SegPlan plan(c.n, c.nframes);
-            CkptHook<RecStoreGlobal<L>> hook(plan, RecStoreGlobal<L>{slot0});
-            const HeadParkGlobal park{slot0 + 32 * R, c.n - 1};
-            FastSweep<L, true, HeadParkGlobal> sw(rb, c, park);
-            sw.run_hooked(hook);
-            if (a.n_out) a.n_out[cfg] = c.nframes;
-            if (a.step_out) a.step_out[cfg] = c.h;
-            if (a.alpha_base) {
-#pragma unroll
-                for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = sw.al[t];
-            }
-            if (a.status) a.status[cfg] = 0;
-            me.n = c.n; me.nframes = c.nframes; me.cfg = cfg; me.h = c.h; me.theta = c.theta;
-            me.T[0] = sw.Qw; me.T[1] = sw.Qx; me.T[2] = sw.Qy; me.T[3] = sw.Qz;
-            me.T[4] = sw.Px; me.T[5] = sw.Py; me.T[6] = sw.Pz;
-            int begin = 0;
-#pragma unroll
-            for (int s = 0; s < L::S; ++s) {
-                me.end[s] = c.end[s];
-                // robot_i.h:1295-1304: section s fills [begin, min(floor(End_s/h), n))
-                int stop = begin;
-                if (begin < c.nframes) {
-                    const double qd = x_div(c.end[s], c.h);
-                    stop = (qd >= 0.0 && qd < (double)c.nframes) ? (int)qd : c.nframes;
-                    if (stop < begin) stop = begin;
-                }
-                me.stop[s] = stop;
-                begin = stop;
-            }
-        }
-    }
-    sh[threadIdx.x] = me;
-    __syncthreads();        // records (global) and sh[] are visible to the whole CTA
-
-    // ---- pass 2: one warp per configuration ---------------------------------------------------
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#if CTRK_BB_EXPERIMENT == 1      /* timing experiment: pass 1 only */
-    if (a.B > 0) return;
-#endif
-    for (int j = 0; j < 32; ++j) {
-        const EmShared& cf = sh[warp * 32 + j];
-        if (cf.nframes == 0) continue;                      // warp-uniform
-        const int n = cf.nframes;
-        const SegPlan plan(cf.n, n);
-        const int k0 = lane * plan.cnt;
-        const int k1 = (k0 + plan.cnt < n) ? k0 + plan.cnt : n;
-        double* slot0 = a.backbone + cf.cfg * 12 * (int64_t)rb.maxs;
-        {
-            Ctl<L> c;
-            c.theta = cf.theta; c.arc_end = 0.0; c.h = cf.h; c.n = cf.n; c.nframes = n; c.status = 0;
-#pragma unroll
-            for (int s = 0; s < L::S; ++s) {
-                c.end[s] = cf.end[s];
-                const double d = x_sub(c.end[s], rb.len[s]);     // as setup_control
-                c.start[s] = (0.0 < d) ? d : 0.0;
-            }
-#pragma unroll
-            for (int t = 0; t < L::T; ++t) c.al[t] = 0.0;
-            double rec[R], head[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int g = 0; g < R; ++g) rec[g] = 0.0;
-            if (k0 < n) {
-                const bool holds_head = (k1 - 1 == cf.n - 1);
-                if (holds_head) ld256cg(slot0 + 32 * R, head[0], head[1], head[2], head[3]);
-                if ((holds_head ? cf.n - 2 : k1 - 1) >= k0) {
-#pragma unroll
-                    for (int g = 0; g < R; g += 4) ld256cg(slot0 + (int64_t)lane * R + g, rec[g], rec[g + 1], rec[g + 2], rec[g + 3]);
-                }
-            }
-            __syncwarp();       // every lane holds its record: the frames may now overwrite that region
-            QT T;
-            T.w = cf.T[0]; T.x = cf.T[1]; T.y = cf.T[2]; T.z = cf.T[3]; T.px = cf.T[4]; T.py = cf.T[5]; T.pz = cf.T[6];
-            emit_run<L>(rb, c, plan, lane, rec, head, T,
-                        FrameStoreGlobal{slot0, a.tip ? a.tip + cf.cfg * 12 : nullptr, n - 1});
-        }
-        if (a.radius) {
-            double* rad = a.radius + cf.cfg * (int64_t)rb.maxs;
-            int    begin = 0;
-            double rsec  = 0.0;
-#pragma unroll
-            for (int s = 0; s < L::S; ++s) {
-                if (begin >= n) continue;
-                rsec = rb.rad[s];
-                const int stop = cf.stop[s];
-                for (int k = begin + lane; k < stop; k += 32) rad[k] = rsec;
-                begin = stop;
-            }
-            __syncwarp();
-            if (lane == 0) rad[n - 1] = rsec;
-        }
-    }
-}
-
-// ---- backbone kernel, SoA layout [MaxS][12][B], FAST arithmetic ---------------------------------
-// With configurations along the fastest axis a thread-per-configuration kernel already writes
-// coalesced (a warp stores 32 x 8 B contiguous per matrix entry), so nothing needs to be parked or
-// handed to other lanes: the thread sweeps twice.  Sweep 1 is the tip solver (total product T);
-// sweep 2 repeats the sweep from the tip and emits Frame_k = Init Rz(alpha_k+theta) I_k with
-// I_{ktip} = T and I_{k-1} = I_k inv(E_k), one sample late so the frame arithmetic overlaps the
-// next sweep step (FastSweep::run_emit).  No shared memory, no scratch traffic at all: DRAM sees
-// the joint values and the output.
+// ---- backbone kernel, FAST arithmetic, every layout: two sweeps per thread -----------------------
+// Frames need the prefix products E_0 ... E_k, the sweep produces sample N-1 first.  Earlier
+// kernels parked every sample in the output region and rebuilt the frames in a second pass
+// (thread-per-configuration: v1; warp-per-configuration with a scan over SE(3) products: v2/v3) or
+// saved 32 sweep states and let the lanes of a warp repeat their run of the sweep (v4); see
+// DESIGN.md §4.3 and profiles/r01_backbone_*.  What won is the simplest scheme: the thread sweeps
+// twice.  Sweep 1 is the tip solver (total product T); sweep 2 repeats the sweep from the tip and
+// emits Frame_k = Init Rz(alpha_k+theta) I_k with I_{ktip} = T and I_{k-1} = I_k inv(E_k), one
+// sample late so the frame arithmetic overlaps the next sweep step (FastSweep::run_emit).  No
+// shared memory, no scratch traffic: DRAM sees the joint values and the output.
+//   SoA [MaxS][12][B]: a warp stores 32 x 8 B contiguous per matrix entry.
+//   AoS [B][MaxS][12]: a thread stores its frame as three full 32-B sectors; consecutive threads
+//   write 96*MaxS bytes apart, which the memory system takes at full speed as long as the
+//   configurations in flight are neighbours (hence window-local binning in step mode; a random
+//   visiting order is 2.8x slower, tools/tune_bb.cu).
 struct FrameStoreSoa {
     double* base;            // backbone + cfg
     int64_t B;
@@ -622,10 +220,23 @@ struct FrameStoreSoa {
         if (k == ktip && tip) store_tf(tip, F);
     }
 };
+template <bool ALIGNED32>
+struct FrameStoreAos {       // one configuration's frames back to back: 3 full-sector stores per frame
+    double* slot0;
+    double* tip;
+    int     ktip;
+    __device__ __forceinline__ void operator()(int k, const double* F) const
+    {
+        if (ALIGNED32) store_tf256(slot0 + (int64_t)k * 12, F);
+        else           store_tf(slot0 + (int64_t)k * 12, F);
+        if (k == ktip && tip) store_tf(tip, F);
+    }
+};
 
-template <class L>
+// LAYOUT: 0 = SoA [MaxS][12][B], 1 = AoS [B][MaxS][12] with a 32-byte aligned buffer, 2 = AoS, 16-byte aligned
+template <class L, int LAYOUT>
 __global__ void __launch_bounds__(kBlock, 4)
-fk_backbone_soa_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
+fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.B) return;
@@ -646,14 +257,22 @@ fk_backbone_soa_kernel(const __grid_constant__ KRobot rb, const __grid_constant_
             for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = s1.al[t];
         }
     }
-    {
+    if (LAYOUT == 0) {
         const FrameStoreSoa fs{a.backbone + cfg, a.B, a.tip ? a.tip + cfg * 12 : nullptr, c.nframes - 1};
         const PendingFrameEmitter<FrameStoreSoa> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
                                                     -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         FastSweep<L, false, PendingFrameEmitter<FrameStoreSoa>> s2(rb, c, em);
         s2.run_emit();
+        if (a.radius) fill_radius<L>(rb, c, a.radius + cfg, a.B);
+    } else {
+        using Store = FrameStoreAos<LAYOUT == 1>;
+        const Store fs{a.backbone + cfg * 12 * (int64_t)rb.maxs, a.tip ? a.tip + cfg * 12 : nullptr, c.nframes - 1};
+        const PendingFrameEmitter<Store> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
+                                            -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        FastSweep<L, false, PendingFrameEmitter<Store>> s2(rb, c, em);
+        s2.run_emit();
+        if (a.radius) fill_radius<L>(rb, c, a.radius + cfg * (int64_t)rb.maxs, 1);
     }
-    if (a.radius) fill_radius<L>(rb, c, a.radius + cfg, a.B);
     if (a.n_out) a.n_out[cfg] = c.nframes;
     if (a.step_out) a.step_out[cfg] = c.h;
     if (a.status) a.status[cfg] = 0;

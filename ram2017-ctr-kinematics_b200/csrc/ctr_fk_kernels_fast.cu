@@ -7,10 +7,15 @@ namespace ctrk {
 
 static inline unsigned grid_for(int64_t B) { return (unsigned)((B + kBlock - 1) / kBlock); }
 
-cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st)
+cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& args, cudaStream_t st)
 {
-    if (a.B <= 0) return cudaSuccess;
-    const unsigned grid = grid_for(a.B);
+    if (args.B <= 0) return cudaSuccess;
+    FkArgs a = args;
+    unsigned grid = grid_for(a.B);
+    if (a.order) {      // window-sorted order: walk the windows rank-major (see fk_tip_kernel)
+        a.windows = (int)((a.B + kBinWindow - 1) / kBinWindow);
+        grid = (unsigned)a.windows * (kBinWindow / kBlock);
+    }
     switch (key) {
 #define X(S, A, Bq, C) CTRK_LAUNCH_CASE(fk_tip_kernel, true, S, A, Bq, C)
         CTRK_FOR_EACH_LAYOUT_K(X)
@@ -25,56 +30,15 @@ cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cud
 {
     if (a.B <= 0) return cudaSuccess;
     const unsigned grid = grid_for(a.B);
-    // AoS: warp-parallel second pass (needs a 32-B aligned buffer for its 256-bit stores)
-    const bool warp_ok = !a.soa && rb.maxs <= kBbMaxSamples && (reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0;
-    // long backbones: checkpointed sweep, frames emitted per run (no per-sample parking round trip)
-    if (warp_ok && rb.maxs >= kCkMinSamples) {
-        const unsigned gridw = (unsigned)((a.B + kCkBlock - 1) / kCkBlock);
-        switch (key) {
-#define X(S, A, Bq, C) \
-    case S * 1000 + A * 100 + Bq * 10 + C: \
-        fk_backbone_emit_kernel<Lay<S, A, Bq, C>><<<gridw, kCkBlock, 0, st>>>(rb, a); \
-        break;
-            CTRK_FOR_EACH_LAYOUT_K(X)
-#undef X
-            default: return cudaErrorInvalidValue;
-        }
-        count_launch();
-        return cudaGetLastError();
-    }
-    if (warp_ok) {
-        const unsigned gridw = (unsigned)((a.B + kBbBlock - 1) / kBbBlock);
-        const size_t smem = sizeof(double) * 4 * (size_t)rb.maxs * kBbBufs * kBbWarps;
-        switch (key) {
-#define X(S, A, Bq, C) \
-    case S * 1000 + A * 100 + Bq * 10 + C: { \
-        /* per device and cheap: set on every launch (above the 48 KB default for MaxSamples > 384) */ \
-        cudaError_t ea = cudaFuncSetAttribute(fk_backbone_warp_kernel<Lay<S, A, Bq, C>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (ea != cudaSuccess) return ea; \
-        fk_backbone_warp_kernel<Lay<S, A, Bq, C>><<<gridw, kBbBlock, smem, st>>>(rb, a); \
-        break; }
-            CTRK_FOR_EACH_LAYOUT_K(X)
-#undef X
-            default: return cudaErrorInvalidValue;
-        }
-        count_launch();
-        return cudaGetLastError();
-    }
-    if (a.soa) {        // two sweeps per thread, frames emitted coalesced across configurations
-        switch (key) {
-#define X(S, A, Bq, C) \
-    case S * 1000 + A * 100 + Bq * 10 + C: \
-        fk_backbone_soa_kernel<Lay<S, A, Bq, C>><<<grid, kBlock, 0, st>>>(rb, a); \
-        break;
-            CTRK_FOR_EACH_LAYOUT_K(X)
-#undef X
-            default: return cudaErrorInvalidValue;
-        }
-        count_launch();
-        return cudaGetLastError();
-    }
+    // one kernel for every layout: two sweeps per thread, frames emitted as the second sweep passes
+    const int layout = a.soa ? 0 : ((reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0 ? 1 : 2);
     switch (key) {
-#define X(S, A, Bq, C) CTRK_LAUNCH_CASE(fk_backbone_kernel, true, S, A, Bq, C)
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: \
+        if (layout == 0)      fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 0><<<grid, kBlock, 0, st>>>(rb, a); \
+        else if (layout == 1) fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 1><<<grid, kBlock, 0, st>>>(rb, a); \
+        else                  fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 2><<<grid, kBlock, 0, st>>>(rb, a); \
+        break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X
         default: return cudaErrorInvalidValue;

@@ -9,14 +9,12 @@ namespace ctrk {
 // In step mode N_c = floor(sum(Phi)/step) differs per configuration (1..MaxSamples).  A warp runs
 // as long as its longest sweep, so configurations are counting-sorted by N_c (longest first) and
 // the solver threads pick their configuration through `order`.  Only the 4-byte index moves.
-//
-// Both passes keep a block-private histogram in shared memory (one CTA covers kBinItems
-// configurations) and touch the global bins once per CTA and bin: with one global atomic per
-// configuration the ~256 hot addresses serialise in L2 (measured: 213 us per pass for 1M
-// configurations, 17 % of the whole step; now a few us).
+// History: one global atomic per configuration serialised on ~256 hot addresses in L2 (213 us per
+// pass for 1M configurations); block-private shared-memory histograms fixed that; the batch-wide
+// sort was then replaced by window-local sorting (below) for the sake of the backbone kernels.
 constexpr int kBinThreads = 256;
-constexpr int kBinPerThread = 16;
-constexpr int kBinItems = kBinThreads * kBinPerThread;
+constexpr int kBinItems = kBinWindow;                       // one CTA sorts one window
+constexpr int kBinPerThread = kBinItems / kBinThreads;
 
 template <class L>
 __device__ __forceinline__ int sample_count_of(const KRobot& rb, const double* __restrict__ jv, int64_t i,
@@ -42,108 +40,75 @@ __device__ __forceinline__ int sample_count_of(const KRobot& rb, const double* _
     return cnt;
 }
 
+// One kernel: every CTA counting-sorts its own window of kBinItems consecutive configurations
+// (longest sweep first) and writes that window of `order`.  Sorting inside windows instead of
+// across the batch keeps the configurations a wave of solver threads touches close together:
+// the backbone kernels write 24.6 KB per configuration, and with a batch-wide sort the ~75 k
+// regions in flight are scattered over the whole output buffer (measured with a random visiting
+// order: 2.8x slower, tools/tune_bb.cu); a window of 4096 configurations costs nothing.  A warp
+// still sees near-uniform sample counts (a window holds 16 configurations per possible count at
+// MaxSamples = 256).  No global atomics, no temporaries besides `order`.
 template <class L>
 __global__ void __launch_bounds__(kBinThreads)
-count_samples_kernel(const __grid_constant__ KRobot rb, const double* __restrict__ jv, int64_t B,
-                     int mode, double step, int nsamples, int32_t* __restrict__ n,
-                     uint32_t* __restrict__ hist, int nbins)
+bin_local_kernel(const __grid_constant__ KRobot rb, const double* __restrict__ jv, int64_t B, int mode,
+                 double step, int nsamples, int32_t* __restrict__ order, int nbins)
 {
-    extern __shared__ uint32_t sh[];
-    for (int b = threadIdx.x; b < nbins; b += kBinThreads) sh[b] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kBinItems;
-#pragma unroll 4
-    for (int j = 0; j < kBinPerThread; ++j) {
-        const int64_t i = base + (int64_t)j * kBinThreads + threadIdx.x;    // coalesced n[] stores
-        if (i < B) {
-            const int cnt = sample_count_of<L>(rb, jv, i, mode, step, nsamples);
-            n[i] = cnt;
-            atomicAdd(&sh[cnt], 1u);
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += kBinThreads)
-        if (sh[b]) atomicAdd(&hist[b], sh[b]);
-}
-
-// hist[0..nbins) -> start offset of each bin when bins are laid out from the LARGEST count down.
-__global__ void bin_offsets_kernel(uint32_t* hist, int nbins)
-{
-    extern __shared__ uint32_t sh[];
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = hist[b];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int b = nbins - 1; b >= 0; --b) {
-            const uint32_t c = sh[b];
-            sh[b] = acc;
-            acc += c;
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) hist[b] = sh[b];
-}
-
-__global__ void __launch_bounds__(kBinThreads)
-bin_scatter_kernel(const int32_t* __restrict__ n, int64_t B, uint32_t* __restrict__ cursor,
-                   int32_t* __restrict__ order, int nbins)
-{
-    extern __shared__ uint32_t sh[];          // [0,nbins): block histogram, then the block's base
-    uint32_t* fill = sh + nbins;              // [nbins, 2 nbins): running rank inside the block
+    extern __shared__ uint32_t sh[];          // [0,nbins): window histogram, then bin offsets
+    uint32_t* fill = sh + nbins;              // [nbins, 2 nbins): running rank inside a bin
     for (int b = threadIdx.x; b < 2 * nbins; b += kBinThreads) sh[b] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kBinItems;
-    int cnt[kBinPerThread];
-#pragma unroll
+    // the count is cheap (one division): it is evaluated again in the scatter pass instead of
+    // being kept in kBinPerThread registers
+#pragma unroll 4
     for (int j = 0; j < kBinPerThread; ++j) {
         const int64_t i = base + (int64_t)j * kBinThreads + threadIdx.x;
-        cnt[j] = (i < B) ? n[i] : -1;
-        if (cnt[j] >= 0) atomicAdd(&sh[cnt[j]], 1u);
+        if (i < B) atomicAdd(&sh[sample_count_of<L>(rb, jv, i, mode, step, nsamples)], 1u);
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += kBinThreads)
-        if (sh[b]) sh[b] = atomicAdd(&cursor[b], sh[b]);      // reserve a contiguous run per bin
-    __syncthreads();
+    if (threadIdx.x < 32) {
+        // exclusive scan from the LARGEST count down, one warp, nbins/32 chunks
+        uint32_t carry = 0;
+        for (int hi = nbins - 1; hi >= 0; hi -= 32) {
+            const int b = hi - (int)threadIdx.x;
+            const uint32_t c = (b >= 0) ? sh[b] : 0u;
+            uint32_t incl = c;
 #pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((int)threadIdx.x >= off) incl += o;
+            }
+            if (b >= 0) sh[b] = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
     for (int j = 0; j < kBinPerThread; ++j) {
-        if (cnt[j] < 0) continue;
         const int64_t i = base + (int64_t)j * kBinThreads + threadIdx.x;
-        const uint32_t r = atomicAdd(&fill[cnt[j]], 1u);
-        order[sh[cnt[j]] + r] = (int32_t)i;
+        if (i >= B) continue;
+        const int cnt = sample_count_of<L>(rb, jv, i, mode, step, nsamples);
+        const uint32_t r = atomicAdd(&fill[cnt], 1u);
+        order[base + sh[cnt] + r] = (int32_t)i;
     }
 }
 
-cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, int64_t B, int mode,
-                                 double step, int nsamples, int32_t* n, uint32_t* hist, cudaStream_t st)
+cudaError_t launch_bin_local(int key, const KRobot& rb, const double* jv, int64_t B, int mode, double step,
+                             int nsamples, int32_t* order, cudaStream_t st)
 {
     if (B <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((B + kBinItems - 1) / kBinItems);
     const int nbins = rb.maxs + 2;
-    const size_t smem = sizeof(uint32_t) * (size_t)nbins;
+    const size_t smem = 2 * sizeof(uint32_t) * (size_t)nbins;
     switch (key) {
 #define X(S, A, Bq, C) \
     case S * 1000 + A * 100 + Bq * 10 + C: \
-        count_samples_kernel<Lay<S, A, Bq, C>><<<grid, kBinThreads, smem, st>>>(rb, jv, B, mode, step, nsamples, n, hist, nbins); \
+        bin_local_kernel<Lay<S, A, Bq, C>><<<grid, kBinThreads, smem, st>>>(rb, jv, B, mode, step, nsamples, order, nbins); \
         break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X
         default: return cudaErrorInvalidValue;
     }
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_bin_offsets(uint32_t* hist, int nbins, cudaStream_t st)
-{
-    bin_offsets_kernel<<<1, 256, sizeof(uint32_t) * (size_t)nbins, st>>>(hist, nbins);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, int nbins, cudaStream_t st)
-{
-    if (B <= 0) return cudaSuccess;
-    bin_scatter_kernel<<<(unsigned)((B + kBinItems - 1) / kBinItems), kBinThreads, 2 * sizeof(uint32_t) * (size_t)nbins, st>>>(n, B, cursor, order, nbins);
     count_launch();
     return cudaGetLastError();
 }

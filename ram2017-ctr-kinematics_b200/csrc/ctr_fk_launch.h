@@ -25,6 +25,8 @@ struct FkArgs {
     double*        backbone;    // [B][maxs][12] or [maxs][12][B]   nullable
     double*        radius;      // [B][maxs]     or [maxs][B]       nullable
     int            soa;         // backbone/radius layout
+    int            windows;     // tip kernels, with `order`: number of binning windows; CTAs then walk the
+                                // windows rank-major (every window's longest sweeps first), 0 = linear
 };
 
 struct JacArgs {
@@ -61,6 +63,7 @@ struct ShootArgs {
 };
 
 constexpr int kBlock = 128;     // threads per CTA for every solver kernel
+constexpr int kBinWindow = 4096;        // step-mode binning sorts windows of this many consecutive configurations
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
 cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
@@ -76,12 +79,10 @@ cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, int s
 // base-angle shooting solve: persistent kernel with a ticket queue (grid sized to the device)
 cudaError_t launch_shoot(int key, const KRobot& rb, const ShootArgs& a, int sm_count, cudaStream_t st);
 
-// step-mode binning: sample count per configuration + histogram, then a counting sort that
-// yields `order` with the longest sweeps first (ctr_fk_kernels_util.cu)
-cudaError_t launch_count_samples(int key, const KRobot& rb, const double* jv, int64_t B, int mode,
-                                 double step, int nsamples, int32_t* n, uint32_t* hist, cudaStream_t st);
-cudaError_t launch_bin_offsets(uint32_t* hist, int nbins, cudaStream_t st);   // in place: descending exclusive scan
-cudaError_t launch_bin_scatter(const int32_t* n, int64_t B, uint32_t* cursor, int32_t* order, int nbins, cudaStream_t st);
+// step-mode binning: `order` = every window of 16384 consecutive configurations counting-sorted by
+// sample count, longest sweeps first (ctr_fk_kernels_util.cu)
+cudaError_t launch_bin_local(int key, const KRobot& rb, const double* jv, int64_t B, int mode, double step,
+                             int nsamples, int32_t* order, cudaStream_t st);
 
 }  // namespace ctrk
 #include "../host/ctr_sampler.h"

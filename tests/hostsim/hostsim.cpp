@@ -157,121 +157,15 @@ extern "C" int hostsim_tangent(const ctr_robot_desc* d, const double* jv, int mo
     }
 }
 
-// Checkpointed sweep (the backbone kernel's scheme) on the CPU build: sweep once saving 32 states,
-// then repeat every run from its state; samples[B][maxs][4] receives what the 32 runs emit.
 namespace {
-struct HeadPark {
-    double* head; int nm1;
-    void operator()(int k, double ux, double uy, double uz, double al) const
-    {
-        if (k == nm1) { head[0] = ux; head[1] = uy; head[2] = uz; head[3] = al; }
-    }
-};
-struct CkStoreHost {
-    double* base; int stride;
-    template <class SW>
-    void operator()(int slot, const SW& sw) const
-    {
-        sw.save_state(base + slot * stride);
-    }
-};
-struct RecStoreHost {        // state + suffix product, the record of emit_run
-    double* base; int stride;
-    template <class SW>
-    void operator()(int slot, const SW& sw) const
-    {
-        sw.save_state(base + slot * stride);
-        sw.suffix_with_pending(base + slot * stride + SW::kStateDoubles);
-    }
-};
 struct FrameStoreHost {
     double* frames;          // [maxs][12]
     void operator()(int k, const double* F) const { std::memcpy(frames + 12 * k, F, 12 * sizeof(double)); }
 };
-template <class L>
-void emit_all(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, double* frames)
-{
-    for (int64_t i = 0; i < B; ++i) {
-        Ctl<L> c;
-        setup_control<L>(rb, jv + i * L::NJ, mode, step, ns, c);
-        if (c.status) continue;
-        constexpr int R = EmitLayout<L>::kStride;
-        double rec[32][R], head[4] = {0, 0, 0, 0};
-        for (auto& r : rec) for (double& x : r) x = 1e300;     // poison
-        SegPlan plan(c.n, c.nframes);
-        RecStoreHost st{&rec[0][0], R};
-        CkptHook<RecStoreHost> hook(plan, st);
-        HeadPark hp{head, c.n - 1};
-        FastSweep<L, true, HeadPark> sw(rb, c, hp);
-        sw.run_hooked(hook);
-        QT T;
-        T.w = sw.Qw; T.x = sw.Qx; T.y = sw.Qy; T.z = sw.Qz; T.px = sw.Px; T.py = sw.Py; T.pz = sw.Pz;
-        Ctl<L> c2 = c;
-        for (int t = 0; t < L::T; ++t) c2.al[t] = 0.0;
-        c2.arc_end = 0.0;
-        FrameStoreHost fs{frames + i * 12 * (int64_t)rb.maxs};
-        for (int lane = 0; lane < 32; ++lane) emit_run<L>(rb, c2, plan, lane, rec[lane], head, T, fs);
-    }
-}
-template <class L>
-void resweep_all(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, double* samples)
-{
-    for (int64_t i = 0; i < B; ++i) {
-        Ctl<L> c;
-        setup_control<L>(rb, jv + i * L::NJ, mode, step, ns, c);
-        if (c.status) continue;
-        double ck[32][2 * L::T], head[4] = {0, 0, 0, 0};
-        for (auto& r : ck) for (double& x : r) x = 1e300;     // poison: unsaved states must not be read
-        SegPlan plan(c.n, c.nframes);
-        CkStoreHost st{&ck[0][0], 2 * L::T};
-        CkptHook<CkStoreHost> hook(plan, st);
-        HeadPark hp{head, c.n - 1};
-        FastSweep<L, false, HeadPark> sw(rb, c, hp);
-        sw.run_hooked(hook);
-        Park park{samples + i * 4 * (int64_t)rb.maxs};
-        // second pass must not depend on the tip angles: wipe them like the kernel does
-        Ctl<L> c2 = c;
-        for (int t = 0; t < L::T; ++t) c2.al[t] = 0.0;
-        c2.arc_end = 0.0;
-        for (int lane = 0; lane < 32; ++lane) resweep_run<L>(rb, c2, plan, lane, ck[lane], head, park);
-    }
-}
 }  // namespace
 
-extern "C" int hostsim_resweep(const ctr_robot_desc* d, const double* jv, int64_t B, int mode, double step, int ns,
-                               double* samples)
-{
-    KRobot rb;
-    int rc = make_krobot(d, &rb);
-    if (rc) return rc;
-    switch (layout_key(d)) {
-#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: resweep_all<Lay<S, A, Bq, C>>(rb, jv, B, mode, step, ns, samples); break;
-        CTRK_FOR_EACH_LAYOUT(X)
-#undef X
-        default: return CTR_FK_E_DESC;
-    }
-    return 0;
-}
-
-// Frame emission from the checkpointed sweep (emit_run, the backbone kernel's scheme):
-// frames[B][maxs][12].
-extern "C" int hostsim_emit(const ctr_robot_desc* d, const double* jv, int64_t B, int mode, double step, int ns,
-                            double* frames)
-{
-    KRobot rb;
-    int rc = make_krobot(d, &rb);
-    if (rc) return rc;
-    switch (layout_key(d)) {
-#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: emit_all<Lay<S, A, Bq, C>>(rb, jv, B, mode, step, ns, frames); break;
-        CTRK_FOR_EACH_LAYOUT(X)
-#undef X
-        default: return CTR_FK_E_DESC;
-    }
-    return 0;
-}
-
-// Thread-per-configuration frame emission (the SoA backbone kernel's scheme): a first sweep for the
-// total product, a second sweep emitting frames one sample late (FastSweep::run_emit).
+// Frame emission of the backbone kernel: a first sweep for the total product, a second sweep
+// emitting frames one sample late (FastSweep::run_emit).
 namespace {
 template <class L>
 void emit_full_all(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, double* frames)

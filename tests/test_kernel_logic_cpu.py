@@ -187,56 +187,22 @@ def test_tangent_sweep_jacobian(ctrfk, oracle, hostsim, robots, name):
 
 
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
-def test_checkpointed_resweep_reproduces_the_sweep(ctrfk, hostsim, robots, name):
-    """The backbone kernel's scheme: sweep once saving 32 states, repeat each run of samples from
-    its state.  The repeated samples must equal the straight sweep's (the only difference is that
-    a resumed run re-evaluates sin/cos of the carried angles: a few ulp)."""
-    import ctypes as C
-    d = robots[name]
-    jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name], 0, 400), util.edge_joint_sets(d)])
-    B = jv.shape[0]
-    hostsim.hostsim_resweep.restype = C.c_int
-    hostsim.hostsim_resweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
-    for mode, step, ns in ((ctrfk.MODE_NSAMPLE, 0.0, 256), (ctrfk.MODE_STEP, d.max_length / 256.0, 0),
-                           (ctrfk.MODE_NSAMPLE, 0.0, 1), (ctrfk.MODE_NSAMPLE, 0.0, 2), (ctrfk.MODE_NSAMPLE, 0.0, 31),
-                           (ctrfk.MODE_NSAMPLE, 0.0, 33), (ctrfk.MODE_NSAMPLE, 0.0, 64), (ctrfk.MODE_NSAMPLE, 0.0, 65),
-                           (ctrfk.MODE_NSAMPLE, 0.0, 225), (ctrfk.MODE_STEP, 0.004, 0), (ctrfk.MODE_STEP, 0.03, 0)):
-        ref = np.full((B, d.max_samples, 4), np.nan)
-        tip = np.zeros((B, 12)); n = np.zeros(B, np.int32); st = np.zeros(B); ab = np.zeros((B, 8))
-        assert hostsim.hostsim_fk(C.addressof(d), jv.ctypes.data, B, mode, step, ns, 1, tip.ctypes.data, n.ctypes.data,
-                                  st.ctypes.data, ab.ctypes.data, ref.ctypes.data) == 0
-        got = np.full((B, d.max_samples, 4), np.nan)
-        assert hostsim.hostsim_resweep(C.addressof(d), jv.ctypes.data, B, mode, step, ns, got.ctypes.data) == 0
-        for i in range(B):
-            nf = n[i]
-            assert np.isfinite(got[i, :nf]).all(), (mode, step, ns, i)
-            assert np.isnan(got[i, nf + 1:]).all()            # nothing beyond the sweep
-            err = np.abs(got[i, :nf] - ref[i, :nf])
-            # curvature relative to the largest component (sin/cos of an angle near 0 carries the
-            # absolute drift of the rotated pair: ~N ulp of 1), angles absolute
-            scale = max(1.0, np.abs(ref[i, :nf, :3]).max())
-            assert (err[:, :3] / scale).max() < 1e-12, (mode, step, ns, i, (err[:, :3] / scale).max())
-            assert err[:, 3].max() < 1e-12, (mode, step, ns, i, err[:, 3].max())
-
-
-@pytest.mark.parametrize("name", util.ROBOT_FILES)
-def test_frame_emission_from_checkpoints_matches_oracle(ctrfk, oracle, hostsim, robots, name):
-    """emit_run (ctr_fk_core.cuh): frames rebuilt per run as T inv(S) and walked downwards must be
-    the oracle's frames — every frame, not only the tip."""
+def test_frame_emission_matches_oracle(ctrfk, oracle, hostsim, robots, name):
+    """FastSweep::run_emit + PendingFrameEmitter (the backbone kernel's second sweep): frames
+    obtained as I_ktip = T, I_{k-1} = I_k inv(E_k) must be the oracle's frames — every frame, not
+    only the tip — including step mode with dropped tip samples and single-sample sweeps."""
     import ctypes as C
     d = robots[name]
     jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name] + 5, 0, 300), util.edge_joint_sets(d)])
     B = jv.shape[0]
-    for fn in (hostsim.hostsim_emit, hostsim.hostsim_emit_full):
-        fn.restype = C.c_int
-        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    hostsim.hostsim_emit_full.restype = C.c_int
+    hostsim.hostsim_emit_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p]
     for mode, step, ns in ((ctrfk.MODE_NSAMPLE, 0.0, 256), (ctrfk.MODE_STEP, d.max_length / 256.0, 0),
                            (ctrfk.MODE_NSAMPLE, 0.0, 1), (ctrfk.MODE_NSAMPLE, 0.0, 2), (ctrfk.MODE_NSAMPLE, 0.0, 31),
                            (ctrfk.MODE_NSAMPLE, 0.0, 33), (ctrfk.MODE_NSAMPLE, 0.0, 64), (ctrfk.MODE_NSAMPLE, 0.0, 65),
                            (ctrfk.MODE_NSAMPLE, 0.0, 225), (ctrfk.MODE_STEP, 0.004, 0), (ctrfk.MODE_STEP, 0.03, 0)):
         o = oracle.fk_batch(d, jv, mode, step=step, nsamples=ns, backbone=True)
-        # per-run emission from saved records (AoS kernel) and full second sweep (SoA kernel)
-        for fn in (hostsim.hostsim_emit, hostsim.hostsim_emit_full):
+        for fn in (hostsim.hostsim_emit_full,):
             got = np.full((B, d.max_samples, 12), np.nan)
             assert fn(C.addressof(d), jv.ctypes.data, B, mode, step, ns, got.ctypes.data) == 0
             worst_p = worst_r = 0.0

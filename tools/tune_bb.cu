@@ -1,12 +1,13 @@
-// tune_bb.cu — standalone tuning harness (not part of the product): times the AoS backbone kernels
-// of ctr_sec3_tub4 (layout 3,2,1,1) on 200 k configurations x 256 frames.
-//   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -DCTRK_CK_CTAS=6 -DCTRK_CK_WARPS=2 \
-//        tools/tune_bb.cu -o tools/tune_bb_6_2 ; tools/tune_bb_6_2 1000000
-// -DCTRK_CK_CTAS=n        register cap of the emit kernel (resident CTAs per SM)
-// -DCTRK_BB_EXPERIMENT=1  pass 1 only;  =2  frames computed but not stored (DESIGN.md §4.3 timings)
+// tune_bb.cu — standalone tuning harness (not part of the product): times the AoS backbone kernel
+// of ctr_sec3_tub4 (layout 3,2,1,1) on B configurations x 256 frames, visiting the configurations
+// in order, in a random order, and shuffled inside windows of 4096 (what step-mode binning does).
+// The parking / warp-scan / checkpoint kernels this file used to compare
+// are in the history: git show 4b28d88:tools/tune_bb.cu
+//   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo tools/tune_bb.cu -o tools/tune_bb ; tools/tune_bb 1000000
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 #include <cuda_runtime.h>
 
 #include "../ram2017-ctr-kinematics_b200/csrc/ctr_fk_kernels.cuh"
@@ -62,32 +63,38 @@ int main(int argc, char** argv)
     CK(cudaMemcpy(djv, jv.data(), sizeof(double) * B * L::NJ, cudaMemcpyHostToDevice));
     a.jv = djv; a.B = B; a.mode = 1; a.nsamples = 256; a.tip = dtip; a.backbone = dbb; a.radius = drad;
 
-    {   // older kernel: per-sample parking
-        const size_t smem = sizeof(double) * 4 * 256 * kBbBufs * kBbWarps;
-        CK(cudaFuncSetAttribute(fk_backbone_warp_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned grid = (unsigned)((B + kBbBlock - 1) / kBbBlock);
-        float ms = time_it([&] { fk_backbone_warp_kernel<L><<<grid, kBbBlock, smem>>>(rb, a); });
-        CK(cudaDeviceSynchronize());
-        printf("parking kernel              %.3f ms  %.3e cfg/s\n", ms, B / (ms * 1e-3));
-    }
     std::vector<double> ref(12 * 256 * 4);
-    CK(cudaMemcpy(ref.data(), dbb + (int64_t)12 * 256 * 1234, sizeof(double) * ref.size(), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(dbb, 0, sizeof(double) * B * 12 * 256));
-    {
-        const size_t smem = 0;
-        cudaFuncAttributes fa;
-        CK(cudaFuncGetAttributes(&fa, fk_backbone_emit_kernel<L>));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk_backbone_emit_kernel<L>, kCkBlock, smem));
-        const unsigned grid = (unsigned)((B + kCkBlock - 1) / kCkBlock);
-        float ms = time_it([&] { fk_backbone_emit_kernel<L><<<grid, kCkBlock, smem>>>(rb, a); });
+    {   // the shipped kernel: two sweeps per thread, AoS stores
+        const unsigned grid = (unsigned)((B + kBlock - 1) / kBlock);
+        CK(cudaMemset(dbb, 0, sizeof(double) * B * 12 * 256));
+        float ms = time_it([&] { fk_backbone_twosweep_kernel<L, 1><<<grid, kBlock>>>(rb, a); });
         CK(cudaDeviceSynchronize());
-        std::vector<double> got(ref.size());
-        CK(cudaMemcpy(got.data(), dbb + (int64_t)12 * 256 * 1234, sizeof(double) * got.size(), cudaMemcpyDeviceToHost));
-        double md = 0;
-        for (size_t i = 0; i < got.size(); ++i) md = fmax(md, fabs(got[i] - ref[i]));
-        printf("emit kernel ctas %2d warps/cta %d  regs %3d local %4zu smem %zu occ %2d CTAs (%2d warps/SM)  %.3f ms  %.3e cfg/s  maxdiff %.2e\n",
-               CTRK_CK_CTAS, kCkWarps, fa.numRegs, fa.localSizeBytes, fa.sharedSizeBytes, occ, occ * kCkWarps, ms, B / (ms * 1e-3), md);
+        CK(cudaMemcpy(ref.data(), dbb + (int64_t)12 * 256 * 1234, sizeof(double) * ref.size(), cudaMemcpyDeviceToHost));
+        printf("two-sweep, AoS stores, configurations in order       %.3f ms  %.3e cfg/s\n", ms, B / (ms * 1e-3));
+    }
+    {   // same kernel, configurations visited in random order (what step-mode binning does to locality)
+        std::vector<int32_t> perm(B);
+        for (int64_t i = 0; i < B; ++i) perm[i] = (int32_t)i;
+        uint64_t x = 88172645463325252ull;
+        for (int64_t i = B - 1; i > 0; --i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; std::swap(perm[i], perm[x % (uint64_t)(i + 1)]); }
+        int32_t* dperm;
+        CK(cudaMalloc(&dperm, sizeof(int32_t) * B));
+        CK(cudaMemcpy(dperm, perm.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice));
+        FkArgs b = a; b.order = dperm;
+        const unsigned grid = (unsigned)((B + kBlock - 1) / kBlock);
+        float ms = time_it([&] { fk_backbone_twosweep_kernel<L, 1><<<grid, kBlock>>>(rb, b); });
+        CK(cudaDeviceSynchronize());
+        printf("two-sweep, AoS stores, random visiting order       %.3f ms  %.3e cfg/s\n", ms, B / (ms * 1e-3));
+        // sorted-within-window order: blocks of 4096 consecutive configurations shuffled internally only
+        for (int64_t i = 0; i < B; ++i) perm[i] = (int32_t)i;
+        for (int64_t b0 = 0; b0 < B; b0 += 4096) {
+            const int64_t e = std::min<int64_t>(B, b0 + 4096);
+            for (int64_t i = e - 1; i > b0; --i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; std::swap(perm[i], perm[b0 + x % (uint64_t)(i - b0 + 1)]); }
+        }
+        CK(cudaMemcpy(dperm, perm.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice));
+        ms = time_it([&] { fk_backbone_twosweep_kernel<L, 1><<<grid, kBlock>>>(rb, b); });
+        CK(cudaDeviceSynchronize());
+        printf("two-sweep, AoS stores, shuffled within 4096-blocks   %.3f ms  %.3e cfg/s\n", ms, B / (ms * 1e-3));
     }
     return 0;
 }
