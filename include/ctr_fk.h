@@ -57,8 +57,7 @@ extern "C" {
 /* flags for ctr_fk_batch* */
 #define CTR_FK_FLAG_STRICT     1u  /* reference operation order, libm-grade sin/cos/div/sqrt   */
 #define CTR_FK_FLAG_NO_BINNING 2u  /* step mode: do not sort configurations by sample count    */
-#define CTR_FK_FLAG_SOA        4u  /* backbone laid out [k][12][B] instead of [B][MaxS][12]:
-                                       the fastest backbone path (coalesced stores, no scratch)  */
+#define CTR_FK_FLAG_SOA        4u  /* backbone laid out [k][12][B] instead of [B][MaxS][12]     */
 
 /* error codes (<0) */
 #define CTR_FK_E_NULL      -1   /* null handle / required pointer                               */
@@ -134,7 +133,7 @@ int ctr_fk_get_desc(ctr_fk_handle h, ctr_robot_desc* out);
  *                                     angles at the base; what calcStability reads, robot_i.h:810)
  *   status    [B]                     out, nullable: CTR_FK_STATUS_* bits
  * jv, tip and backbone must be 16-byte aligned (CTR_FK_E_ARG otherwise); a 32-byte aligned
- * backbone buffer selects the fastest backbone kernel.
+ * backbone buffer lets the frames go out as full-sector 256-bit stores.
  */
 int ctr_fk_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                  int32_t nsamples, uint32_t flags,
