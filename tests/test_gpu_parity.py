@@ -323,6 +323,56 @@ def test_full_size_properties_1M(ctrfk, oracle, robots, engines):
     assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
 
 
+@pytest.mark.parametrize("soa", [False, True], ids=["aos", "soa"])
+def test_backbone_full_size_properties(ctrfk, oracle, robots, engines, soa):
+    """BASELINE config 4 at bench size (ctr_sec3_tub4, 200 k configurations x 256 frames, 4.9 GB):
+    properties that do not need the oracle on every frame — orthonormal rotations, distance from
+    the entry point growing by at most one arc-length step per sample, last frame = tip output, radius from the
+    descriptor, AoS and SoA outputs identical — plus a slice against the oracle."""
+    name = "ctr_sec3_tub4.xml"
+    d, eng = robots[name], engines[name]
+    B, N = 200_000, 256
+    st = torch.cuda.current_stream().cuda_stream
+    jv = torch.empty(B, d.njoints, dtype=torch.float64, device="cuda")
+    eng.sample_joints(util.SEEDS[name], 0, B, jv, st)
+    tip = torch.empty(B, 12, dtype=torch.float64, device="cuda")
+    step_out = torch.empty(B, dtype=torch.float64, device="cuda")
+    bb = torch.empty((N, 12, B) if soa else (B, N, 12), dtype=torch.float64, device="cuda")
+    rd = torch.empty((N, B) if soa else (B, N), dtype=torch.float64, device="cuda")
+    eng.batch(jv, B, 1, nsamples=N, flags=ctrfk.FLAG_SOA if soa else 0, tip=tip, backbone=bb, radius=rd,
+              step_out=step_out, stream=st)
+    torch.cuda.synchronize()
+    F = bb.permute(2, 0, 1) if soa else bb                          # [B, N, 12] view
+    assert torch.isfinite(F).all()
+    assert torch.equal(F[:, N - 1, :], tip)
+    h = step_out
+    p_init = torch.tensor(list(d.init_trafo)[9:], dtype=torch.float64, device="cuda")
+    worst_orth = 0.0
+    for lo in range(0, B, 25_000):                                   # chunks: keep temporaries small
+        f = F[lo:lo + 25_000]
+        R = f[..., :9].reshape(-1, N, 3, 3)                          # column-major: R[..., j, i] = R_ij
+        RtR = torch.einsum("bkji,bkli->bkjl", R, R)
+        worst_orth = max(worst_orth, float((RtR - torch.eye(3, dtype=torch.float64, device="cuda")).abs().max()))
+        # every frame carries its own twist Rz(alpha_k + theta) (robot_i.h:714), so consecutive
+        # positions are not one chord apart; their distance from the entry point is twist-invariant
+        # and grows by at most one arc-length step per sample
+        dist = (f[..., 9:] - p_init).norm(dim=2)
+        assert bool(((dist[:, 1:] - dist[:, :-1]).abs() <= h[lo:lo + 25_000, None] * (1 + 1e-9) + 1e-15).all())
+        assert bool((dist[:, 0] <= h[lo:lo + 25_000] * (1 + 1e-9) + 1e-15).all())
+    assert worst_orth < 1e-12
+    radii = torch.tensor(sorted({d.sec[s].radius[0] for s in range(d.nsections)}), dtype=torch.float64, device="cuda")
+    R_ = rd.permute(1, 0) if soa else rd
+    assert bool(torch.isin(R_, radii).all())
+    sl = slice(123_000, 123_000 + 300)
+    q = jv[sl].cpu().numpy()
+    o = oracle.fk_batch(d, q, 1, nsamples=N, backbone=True, radius=True)
+    got = F[sl].cpu().numpy()
+    for i in range(q.shape[0]):
+        dp, ang = util.pose_errors(o["backbone"][i], got[i])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+    assert np.array_equal(o["radius"], R_[sl].cpu().numpy())
+
+
 def test_single_tube_closed_form_on_gpu(ctrfk, dev):
     """K1 through the CUDA path: one CC tube -> circular arc, independent of N."""
     d = ctrfk.RobotDesc()
