@@ -645,12 +645,16 @@ CTR_HD void se3_step_fast(double ux, double uy, double uz, double h, double ztol
 //     instead of being re-evaluated (15 instead of 22 FP64 instructions per tube and step).  The
 //     rotation is accurate to 1 ulp per step; over N steps that adds O(N) ulp to quantities whose
 //     own rounding history (alpha_t += d_t) is of the same size.
-// A body iteration is HOT when every tube has |d_t| < 2^-4, and the pending sample has
+// A body iteration is HOT when every tube has |d_t| < 0.09375 (kRotMaxHi), and the pending sample has
 // ztol <= |u| and (h|u|/2)^2 < 2^-8; all benchmark workloads are 100 % hot.  Anything else (coarse
 // sampling, zero curvature) takes the generic iteration.
 #ifdef CTRK_COUNT_COLD
 static long long g_iter_total = 0, g_iter_cold = 0, g_iter_cold_delta = 0;
 #endif
+// Carried sin/cos are rotated by the step increment d with the degree-8/9 Taylor pair while
+// |d| < 0.09375 (high word of 1.5 * 2^-4): truncation d^10/10! < 1.5e-17, d^11/11! < 2e-19.
+constexpr int kRotMaxHi = 0x3fb80000;
+
 // C++14 stand-in for `if constexpr`: only functors used with EMIT need emit_hot/emit_generic
 template <bool EMIT, bool HOT> struct EmitPending { template <class F> static CTR_HD void call(F&) {} };
 template <> struct EmitPending<true, true>  { template <class F> static CTR_HD void call(F& f) { f.emit_hot(); } };
@@ -889,7 +893,7 @@ struct FastSweep {
                     amax = a > amax ? a : amax;
                 }
                 const bool eh = on_sample.pending_hot();
-                if (eh && dmax < 0x3fb00000)                           step<false, false, true, true, true>(k, dl, 0.0, 0.0);
+                if (eh && dmax < kRotMaxHi)                            step<false, false, true, true, true>(k, dl, 0.0, 0.0);
                 else if (eh && amax < 0x408f0000 && dmax < 0x40300000) step<false, false, true, false, true>(k, dl, 0.0, 0.0);
                 else                                                   step<false, false, false, false, true>(k, dl, 0.0, 0.0);
             }
@@ -931,7 +935,7 @@ struct FastSweep {
             const double n2  = x_fma(puz, puz, sxy);
             const double m   = n2 * kc.hh2;
             const bool se3_hot = !want_tip || (le_nonneg(kc.ztol2, n2) && hi_word(m) < 0x3f700000);
-            const bool rot_ok  = dmax < 0x3fb00000;          // every |d_t| < 2^-4
+            const bool rot_ok  = dmax < kRotMaxHi;           // every |d_t| < 0.09375
             const bool sc_ok   = amax < 0x408f0000;          // every |alpha_t| < 992 (+ |d_t| stays < 1024)
 #ifdef CTRK_COUNT_COLD   /* host-side analysis builds only (tests/hostsim) */
             ++g_iter_total; if (!(se3_hot && (rot_ok || sc_ok))) ++g_iter_cold;
@@ -1065,7 +1069,7 @@ CTR_HD void sweep_tangent(const KRobot& rb, const Ctl<L>& c, double* base, doubl
         for (int t = 1; t < T; ++t) {
             const double d = c.h * (uz[t] - z0);
             al[t] = al[t] + d;
-            if ((hi_word(d) & 0x7fffffff) < 0x3fb00000) {          // |d| < 2^-4: rotate (as FastSweep::step)
+            if ((hi_word(d) & 0x7fffffff) < kRotMaxHi) {           // rotate (as FastSweep::step)
                 const double d2 = d * d;
                 double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
                 double ps = x_fma(CTRK_FC.qb4[0], d2, CTRK_FC.qb4[1]);

@@ -201,3 +201,11 @@ extern "C" int hostsim_emit_full(const ctr_robot_desc* d, const double* jv, int6
     }
     return 0;
 }
+
+#ifdef CTRK_COUNT_COLD   // analysis build (tools/tier_shares.py): how many sweep iterations left the hot form
+extern "C" void hostsim_tier_counters(long long* out3, int reset)
+{
+    out3[0] = g_iter_total; out3[1] = g_iter_cold; out3[2] = g_iter_cold_delta;
+    if (reset) g_iter_total = g_iter_cold = g_iter_cold_delta = 0;
+}
+#endif
