@@ -1,0 +1,1 @@
+#include "../mini_erl.h"

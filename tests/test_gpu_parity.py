@@ -521,31 +521,7 @@ def test_cpp_host_binary_config1(ctrfk, oracle, robots, dev):
     assert np.abs(np.array([float(x) for x in m.group(2).split(",")]) - r1["tip"][9:]).max() < util.TOL_POS
 
 
-def random_robot(ctrfk, rng, ntubes, max_samples=128):
-    """A random but physically sensible robot with the given tubes-per-section layout."""
-    d = ctrfk.RobotDesc()
-    d.nsections = len(ntubes)
-    d.max_samples = max_samples
-    A = rng.normal(size=(3, 3))
-    Q, _ = np.linalg.qr(A)
-    if np.linalg.det(Q) < 0:
-        Q[:, 0] = -Q[:, 0]
-    t = list(Q.T.reshape(-1)) + list(rng.uniform(-0.1, 0.1, 3))        # column-major rotation + translation
-    for i in range(12):
-        d.init_trafo[i] = t[i]
-    for s, n in enumerate(ntubes):
-        d.sec[s].ntube = n
-        d.sec[s].length = rng.uniform(0.02, 0.08)
-        for k in range(n):
-            d.sec[s].stiffness[k] = rng.uniform(0.05, 6.0)
-            d.sec[s].curvature[k] = rng.uniform(1.0, 60.0)
-            d.sec[s].radius[k] = rng.uniform(3e-4, 2e-3)
-            d.sec[s].poisson[k] = rng.uniform(0.2, 0.45)               # distinct per tube: exercises the
-    return d                                                           # last-VC-section quirk (section_i.h:273)
-
-
-ALL_LAYOUTS = [(1,), (2,), (1, 1), (1, 2), (2, 1), (2, 2), (1, 1, 1), (1, 1, 2), (1, 2, 1), (1, 2, 2),
-               (2, 1, 1), (2, 1, 2), (2, 2, 1), (2, 2, 2)]
+random_robot, ALL_LAYOUTS = util.random_robot, util.ALL_LAYOUTS
 
 
 @pytest.mark.parametrize("layout", ALL_LAYOUTS, ids=["-".join(map(str, l)) for l in ALL_LAYOUTS])
