@@ -137,22 +137,54 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference_rate(desc, a, nthreads, sample, seed, repeat=1):
-    """Times the CPU oracle (a restatement of the reference FK; the reference itself cannot be
-    built here) on `sample` configurations of the bench workload."""
+_REF_ROBOTS = {}
+
+
+def cpu_arm(a):
+    """Which CPU implementation the baseline legs time: ("reference", robot) when oracle/_ref/libctr_ref.so
+    exists — the reference's own sources compiled against stand-in third-party headers (oracle/Makefile
+    target `ref`; prebuilt, it travels to the GPU box) — else ("port", None): the C oracle."""
     import ctrfk
-    import oracle_lib
+    import ref_lib
+    if not os.path.exists(ref_lib.LIB_PATH):
+        return "port", None
+    key = (a.robot, a.max_samples)
+    if key not in _REF_ROBOTS:      # CTR::Robot<double>(MaxSample, XmlFilename), ctr_robot.h:105
+        _REF_ROBOTS[key] = ref_lib.RefRobot.from_xml(ctrfk.resource(a.robot), a.max_samples)
+    return "reference", _REF_ROBOTS[key]
+
+
+def cpu_reference_rate(desc, a, nthreads, sample, seed, repeat=1):
+    """Times the reference's CPU forward kinematics on `sample` configurations of the bench workload:
+    CTR::Robot<double>::calcKinematic through oracle/_ref when that library exists, else the oracle port.
+    One robot object per thread, OpenMP over configurations."""
+    import ctrfk
+    kind, ref = cpu_arm(a)
     jv = ctrfk.sample_joints_host(desc, seed, 0, sample)
     mode = ctrfk.MODE_NSAMPLE if a.mode == "F" else ctrfk.MODE_STEP
     kw = dict(nsamples=a.nsamples, step=desc.max_length / a.nsamples, nthreads=nthreads,
               backbone=a.backbone, radius=a.backbone)
+    if kind == "reference":
+        call = lambda: ref.fk_batch(jv, mode, **kw)
+    else:
+        import oracle_lib
+        call = lambda: oracle_lib.fk_batch(desc, jv, mode, **kw)
     best = None
     for _ in range(repeat):
         t0 = time.perf_counter()
-        oracle_lib.fk_batch(desc, jv, mode, **kw)
+        call()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return sample / best, best
+
+
+CPU_ARM_NOTE = {
+    "reference": "the reference's own sources (ctr_source/*.h, ctr_robot.cpp) compiled -O2 against stand-in "
+                 "Eigen/Erl/Boost headers (oracle/_ref/libctr_ref.so), CTR::Robot<double>::calcKinematic, "
+                 "one robot per thread, OpenMP over configurations",
+    "port": "CPU oracle = step-for-step C restatement of the reference FK (oracle/ctr_oracle.c; "
+            "oracle/_ref/libctr_ref.so not present), OpenMP over configurations",
+}
 
 
 def run_reference(a):
@@ -161,8 +193,8 @@ def run_reference(a):
     if rank != 0:
         return 0
     import ctrfk
-    import oracle_lib
     desc = ctrfk.desc_from_xml(ctrfk.resource(a.robot), a.max_samples)
+    kind, _ = cpu_arm(a)
     threads = host_threads()
     seed = 20171
     # bounded sample per step: ~1 s of CPU work, so K+W steps end within minutes
@@ -179,9 +211,8 @@ def run_reference(a):
             "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "robot": a.robot, "mode": a.mode, "nsamples": a.nsamples,
-                       "note": "CPU oracle = step-for-step C restatement of the reference FK (the reference "
-                               "needs Eigen/Erl/Boost and cannot be built offline); OpenMP over configurations"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                       "note": CPU_ARM_NOTE[kind]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": "%d configurations per step of the bench workload" % sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -401,11 +432,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.shoot:
         threads = host_threads()
+        kind, _ = cpu_arm(a)
         r1, _ = cpu_reference_rate(desc, a, 1, 2048, seed)
         sample = a.cpu_sample or int(min(B, max(20000, r1 * threads * 10.0)))      # ~10 s of CPU work
         rate, secs = cpu_reference_rate(desc, a, threads, sample, seed)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d configurations of the bench workload, %.1f s, OpenMP oracle (oracle/ctr_oracle.c)" % (sample, secs),
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%d configurations of the bench workload, %.1f s; %s" % (sample, secs, CPU_ARM_NOTE[kind]),
                "single_thread_value": r1}
 
     if rank == 0:

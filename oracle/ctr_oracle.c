@@ -1,6 +1,6 @@
 /* ctr_oracle.c — CPU oracle: plain-C restatement of the reference FK.  TEST INFRASTRUCTURE ONLY
- * (see ctr_oracle.h: PARITY UNPINNED — no reference goldens exist and the reference cannot be
- * built here).
+ * (see ctr_oracle.h: pinned bit for bit against the reference's own sources built with stand-in
+ * third-party headers, oracle/_ref; Erl's semantics remain assumed).
  *
  * Build with -ffp-contract=off: the reference is built by CMake without -march (CMakeLists.txt:6,
  * :36-39), i.e. baseline x86-64 without FMA, so every a*b+c below rounds twice.

@@ -3,12 +3,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libctrfk.so) never links, loads or calls it.
  *
- * PARITY UNPINNED: the reference (RViMLab/RAM2017-CTR-kinematics) ships no tests, golden vectors
- * or fixtures for this path, and it cannot be compiled here (Eigen 3.3.3, Erl and Boost
- * property_tree are fetched from the network by install.sh:41,49,59 and are absent).  This file
- * is a step-for-step restatement of robot_i.h / section_i.h; it is pinned only against (a) an
- * independent pure-Python restatement (oracle/ctr_oracle_py.py), (b) the sanity vectors of
- * SURVEY.md §9.2 and (c) closed-form known-answer tests (tests/test_oracle.py).
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN CODE, modulo Erl: the reference ships no tests, golden
+ * vectors or fixtures, but its sources compile here against stand-in headers for its three absent
+ * third-party dependencies (oracle/shim; recipe: oracle/Makefile target `ref` -> oracle/_ref/
+ * libctr_ref.so).  This file's outputs equal that library's BIT FOR BIT — sample counts, steps,
+ * every frame of every sample, radii, Jacobians, stability verdicts, on random and edge inputs, all
+ * 14 section layouts (tests/test_reference_build.py; committed outputs of the reference build:
+ * tests/golden/reference_golden.npz).  Still assumed, because Erl's source is unavailable (unpinned
+ * gitlab HEAD, install.sh:41): Transform/Rotmat constructor argument order, the SE(3) product,
+ * Erl::equal's tolerance, nearestOrthogonal (the [ASSUMED] items of oracle/shim/mini_erl.h).
+ * Further pins: an independent pure-Python restatement (oracle/ctr_oracle_py.py), the sanity
+ * vectors of SURVEY.md §9.2 and closed-form known-answer tests (tests/test_oracle.py).
  */
 #ifndef CTR_ORACLE_H
 #define CTR_ORACLE_H

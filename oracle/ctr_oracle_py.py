@@ -1,8 +1,7 @@
 """Second, independent restatement of the reference FK in pure Python.  TEST INFRASTRUCTURE ONLY.
 
-Purpose: pin oracle/ctr_oracle.c.  The reference ships no golden vectors and cannot be built
-here (PARITY UNPINNED, see ctr_oracle.h), so the C oracle is checked against this file, which
-was written from the mathematics of the reference rather than from the C code:
+Purpose: a second pin of oracle/ctr_oracle.c next to the reference build (oracle/_ref, see
+ctr_oracle.h).  The reference ships no golden vectors; this file was written from the mathematics of the reference rather than from the C code:
 per-tube Python lists, 3x3 row-major matrices + translation vectors instead of flat column-major
 arrays, an explicit list of samples instead of in-place slots.  Two independently written
 restatements agreeing to ~1e-15 is the evidence that both follow robot_i.h / section_i.h.

@@ -1,9 +1,9 @@
 """Freezes outputs of the CPU oracle (oracle/ctr_oracle.c) as regression vectors:
 tests/golden/oracle_golden.npz.
 
-NOT reference-derived: the reference cannot be built in this environment and ships no golden
-vectors (see oracle/ctr_oracle.h, PARITY UNPINNED).  These vectors pin the oracle against silent
-drift and give the GPU box fixed inputs/outputs that do not depend on the oracle being rebuilt.
+NOT reference-derived (the reference-derived vectors are tests/golden/reference_golden.npz, made by
+make_reference_golden.py from the reference build oracle/_ref).  These vectors pin the oracle
+against silent drift and give the GPU box fixed inputs/outputs that do not depend on the oracle being rebuilt.
 Inputs: counter-based sampler (include/ctr_fk.h, ctr_fk_sample_joints_host), seeds of SURVEY §8d,
 first 256 configurations per robot, MaxSamples = 256; mode F: N = 256; mode S: step = MaxLength/256.
 

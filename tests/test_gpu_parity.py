@@ -106,6 +106,68 @@ def test_golden_vectors(ctrfk, robots, engines):
 
 
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_parity_with_the_reference_build(ctrfk, oracle, robots, engines, name):
+    """The CUDA path against the reference's own code running on this box (oracle/_ref/libctr_ref.so, built
+    in the container from /root/reference/ctr_source and shipped prebuilt): 200k configurations per robot and
+    mode through CTR::Robot<double>::calcKinematic; the oracle must equal it bit for bit here too."""
+    import ref_lib
+    if not os.path.exists(ref_lib.LIB_PATH):
+        pytest.skip("oracle/_ref/libctr_ref.so did not travel to this box")
+    d = robots[name]
+    ref = ref_lib.RefRobot.from_desc(d)
+    B = 200_000
+    jv = ctrfk.sample_joints_host(d, util.SEEDS[name] + 100, 0, B)
+    for tag, mode, kw in MODES:
+        kw = kw or dict(step=d.max_length / 256.0)
+        r = ref.fk_batch(jv, mode, **kw)
+        o = oracle.fk_batch(d, jv, mode, **kw)
+        assert np.array_equal(r["tip"], o["tip"]) and np.array_equal(r["n"], o["n"]) and np.array_equal(r["step"], o["step"])
+        g = run_gpu(ctrfk, engines[name], jv, mode, **kw)
+        assert np.array_equal(g["n"], r["n"]) and np.array_equal(g["step"], r["step"])
+        dp, ang = util.pose_errors(r["tip"], g["tip"])
+        print("%s %s vs reference build: %.2e m, %.2e rad" % (name, tag, dp.max(), ang.max()))
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+
+
+def test_reference_golden_gpu(ctrfk, robots, dev):
+    """The CUDA path against numbers the REFERENCE ITSELF produced (tests/golden/reference_golden.npz,
+    generated by tests/golden/make_reference_golden.py from oracle/_ref): sample count and step exact,
+    tip and probed backbone frames within the gate, radius exact, Jacobian and stability verdicts."""
+    g = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+    for name in util.ROBOT_FILES:
+        key = name.replace(".xml", "")
+        d = ctrfk.RobotDesc.from_buffer_copy(bytes(robots[name]))
+        for i in range(12):
+            d.init_trafo[i] = g[key + "/init"][i]
+        eng = ctrfk.Engine(d, 0)
+        jv = g[key + "/jv"]
+        for tag, mode in (("F", 1), ("S", 0)):
+            for flags in (0, 1):
+                r = run_gpu(ctrfk, eng, jv, mode, flags=flags, backbone=True, radius=True, step=d.max_length / 256.0, nsamples=256)
+                assert np.array_equal(r["n"], g["%s/%s/n" % (key, tag)])
+                assert np.array_equal(r["step"], g["%s/%s/step" % (key, tag)])
+                dp, ang = util.pose_errors(r["tip"], g["%s/%s/tip" % (key, tag)])
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+                idx = g["%s/%s/probe_idx" % (key, tag)].astype(np.int64)
+                got = np.take_along_axis(r["backbone"], idx[:, :, None], axis=1)
+                dp, ang = util.pose_errors(got.reshape(-1, 12), g["%s/%s/probe_frames" % (key, tag)].reshape(-1, 12))
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+                live = np.arange(256)[None, :] < r["n"][:, None]
+                assert np.array_equal(r["radius"].astype(np.float32)[live], g["%s/%s/radius" % (key, tag)][live])
+        jac = np.zeros((16, d.njoints, 6)); tip = np.zeros((16, 12))
+        eng.jacobian_host(np.ascontiguousarray(jv[:16]), 16, 128, 1e-5, 1e-4, jac, tip)
+        assert np.abs(jac - g[key + "/jac"]).max() < 1e-6
+        jq = torch.from_numpy(np.ascontiguousarray(jv[:32])).cuda()
+        stable = torch.full((32,), 9, dtype=torch.int32, device="cuda")
+        degree = torch.zeros(32, dtype=torch.float64, device="cuda")
+        eng.stability(jq, 32, 0.2, d.max_length / 128.0, -1.0, stable, degree, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(stable.cpu().numpy(), g[key + "/stable"].astype(np.int32))
+        assert np.abs(degree.cpu().numpy() - g[key + "/degree"]).max() < 1e-7
+        eng.close()
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
 def test_edge_cases(ctrfk, oracle, robots, engines, name):
     d = robots[name]
     jv = util.edge_joint_sets(d)

@@ -1,8 +1,10 @@
-"""Pins the CPU oracle (oracle/ctr_oracle.c).  The reference has no tests or golden vectors for
-this path and cannot be compiled here, so the pins are: (a) SURVEY §9.2 sanity vectors from an
+"""Pins the CPU oracle (oracle/ctr_oracle.c).  The reference has no tests or golden vectors of its
+own for this path, so the pins are: (0) outputs of the reference's own code, built from its sources
+against stand-in third-party headers (tests/golden/reference_golden.npz, test_reference_golden;
+live comparison in tests/test_reference_build.py), (a) SURVEY §9.2 sanity vectors from an
 independent transliteration, (b) a second independent restatement in pure Python
 (oracle/ctr_oracle_py.py), (c) closed-form known-answer tests K1-K6 of SURVEY §4, (d) frozen
-regression vectors."""
+regression vectors of the oracle."""
 import copy
 import json
 import os
@@ -77,6 +79,44 @@ def test_golden_regression(ctrfk, oracle, robots):
             assert np.array_equal(r["step"], g["%s/%s/step" % (key, tag)])
             assert np.abs(r["tip"] - g["%s/%s/tip" % (key, tag)]).max() < 1e-13
             assert np.abs(r["alpha_base"] - g["%s/%s/alpha_base" % (key, tag)]).max() < 1e-12
+
+
+def golden_desc(ctrfk, robots, g, name):
+    """Descriptor of the robot with the entry frame exactly as the reference's XML reader produced it."""
+    d = ctrfk.RobotDesc.from_buffer_copy(bytes(robots[name]))
+    init = g[name.replace(".xml", "") + "/init"]
+    assert np.abs(init - np.array(list(d.init_trafo))).max() < 1e-15      # ctr_fk_orthogonalize agrees to rounding
+    for i in range(12):
+        d.init_trafo[i] = init[i]
+    return d
+
+
+def test_reference_golden(ctrfk, oracle, robots):
+    """tests/golden/reference_golden.npz holds outputs of the reference's own code (oracle/_ref, see
+    tests/golden/make_reference_golden.py).  The oracle reproduces every stored number bit for bit."""
+    g = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+    for name in util.ROBOT_FILES:
+        key = name.replace(".xml", "")
+        d = golden_desc(ctrfk, robots, g, name)
+        jv = g[key + "/jv"]
+        for tag, mode in (("F", ctrfk.MODE_NSAMPLE), ("S", ctrfk.MODE_STEP)):
+            r = oracle.fk_batch(d, jv, mode, step=d.max_length / 256.0, nsamples=256, nthreads=2, backbone=True, radius=True)
+            assert np.array_equal(r["n"], g["%s/%s/n" % (key, tag)])
+            assert np.array_equal(r["step"], g["%s/%s/step" % (key, tag)])
+            assert np.array_equal(r["tip"], g["%s/%s/tip" % (key, tag)])
+            idx = g["%s/%s/probe_idx" % (key, tag)]
+            assert np.array_equal(np.take_along_axis(r["backbone"], idx[:, :, None].astype(np.int64), axis=1),
+                                  g["%s/%s/probe_frames" % (key, tag)])
+            live = np.arange(256)[None, :] < r["n"][:, None]
+            assert np.array_equal(r["radius"].astype(np.float32)[live], g["%s/%s/radius" % (key, tag)][live])
+        for i, q in enumerate(jv[:16]):
+            assert np.array_equal(oracle.jacobian(d, q, 128, 1e-5, 1e-4)[0], g[key + "/jac"][i])
+        for i, q in enumerate(jv[:32]):
+            assert oracle.stability(d, q, 0.2, d.max_length / 128.0) == g[key + "/stable"][i]
+            assert oracle.degree_stability(d, q, 0.2, d.max_length / 128.0, -1.0)[0] == g[key + "/degree"][i]
+        # construction-time call of the XML path (ctr_static.h:248-252)
+        c = oracle.fk_one(d, g[key + "/ctor/jv"], ctrfk.MODE_STEP, step=d.max_length / 256.0)
+        assert c["n"] == g[key + "/ctor/n"] and np.array_equal(c["tip"], g[key + "/ctor/tip"])
 
 
 def single_cc_desc(ctrfk, kappa=40.0, length=0.08):
