@@ -184,3 +184,50 @@ int ctr_ref_max_threads(void)
 }
 
 }  // extern "C"
+
+// ---- sampling scale policies (transrotscale.h), driven with caller-supplied uniform variates ----------
+#include "transrotscale.h"
+
+extern "C" {
+
+// GammaCorrection<double, LookUpSize>::scaleTrans (transrotscale.h:106-122) after set_scale(gamma).
+// lut_size must be one of the instantiated sizes: 0 (closed form), 16, 64, 256, 1024.
+int ctr_ref_gamma_scale(int lut_size, double gamma, const double* u, int64_t n, double* out)
+{
+#define CTR_REF_GAMMA_CASE(L)                                        \
+    case L: {                                                        \
+        CTR::GammaCorrection<double, L> g;                           \
+        g.set_scale(gamma);                                          \
+        for (int64_t i = 0; i < n; ++i) out[i] = g.scaleTrans(u[i]); \
+        return 0;                                                    \
+    }
+    switch (lut_size) {
+        CTR_REF_GAMMA_CASE(0)
+        CTR_REF_GAMMA_CASE(16)
+        CTR_REF_GAMMA_CASE(64)
+        CTR_REF_GAMMA_CASE(256)
+        CTR_REF_GAMMA_CASE(1024)
+        default: return -2;
+    }
+#undef CTR_REF_GAMMA_CASE
+}
+
+// ProportionalScale<double> (transrotscale.h:139-309): initialize(robot), set_scale(p0, p1), then one
+// scaleTrans call per section and configuration, u[B][nsections] -> out[B][nsections].  The first
+// configuration's goal comes from std::rand() inside set_scale (:186-188); goal_first returns it
+// (get_scale()) so that a caller can reproduce it.
+int ctr_ref_proportional_scale(void* h, double p0, double p1, const double* u, int64_t B, double* out, double* goal_first)
+{
+    RefRobot* r = static_cast<RefRobot*>(h);
+    if (!r || !r->init()) return -1;
+    CTR::ProportionalScale<double> ps;
+    if (!ps.initialize(*r)) return -1;
+    ps.set_scale(p0, p1);
+    if (goal_first) *goal_first = ps.get_scale();
+    const int S = int(r->getNSections());
+    for (int64_t i = 0; i < B; ++i)
+        for (int s = 0; s < S; ++s) out[i * S + s] = ps.scaleTrans(u[i * S + s]);
+    return 0;
+}
+
+}  // extern "C"

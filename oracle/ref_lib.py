@@ -49,6 +49,8 @@ def load():
         lib.ctr_ref_degree_stability.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P]
         lib.ctr_ref_random_joints.argtypes = [_P, C.c_int64, _P]
         lib.ctr_ref_max_threads.restype = C.c_int
+        lib.ctr_ref_gamma_scale.argtypes = [C.c_int, C.c_double, _P, C.c_int64, _P]
+        lib.ctr_ref_proportional_scale.argtypes = [_P, C.c_double, C.c_double, _P, C.c_int64, _P, _P]
         _lib = lib
     return _lib
 
@@ -135,3 +137,24 @@ class RefRobot:
 
 def max_threads():
     return load().ctr_ref_max_threads()
+
+
+def gamma_scale(lut_size, gamma, u):
+    """GammaCorrection<double, lut_size>::scaleTrans after set_scale(gamma) (transrotscale.h:106-122)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros_like(u)
+    rc = load().ctr_ref_gamma_scale(lut_size, gamma, u.ctypes.data, u.size, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("reference gamma_scale error %d (table size not instantiated?)" % rc)
+    return out
+
+
+def proportional_scale(robot, p0, p1, u):
+    """ProportionalScale<double> (transrotscale.h:139-309) on u[B][nsections]; returns (scaled, first goal scale)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros_like(u)
+    g = C.c_double()
+    rc = load().ctr_ref_proportional_scale(robot.h, p0, p1, u.ctypes.data, u.shape[0], out.ctypes.data, C.addressof(g))
+    if rc != 0:
+        raise RuntimeError("reference proportional_scale error %d" % rc)
+    return out, g.value

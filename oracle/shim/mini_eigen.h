@@ -274,7 +274,9 @@ public:
     Matrix& setLinSpaced(Index n, T lo, T hi)
     {
         m_storage.resize(R == Dynamic ? n : R, C == Dynamic ? (R == Dynamic ? 1 : n) : C);
-        for (Index i = 0; i < n; ++i) data()[i] = (n == 1) ? hi : lo + (hi - lo) * T(i) / T(n - 1);
+        // Eigen 3.3 linspaced_op for floating point with |hi| >= |lo|: low + i * step, last element = high
+        const T stepv = (n == 1) ? T(1) : (hi - lo) / T(n - 1);
+        for (Index i = 0; i < n; ++i) data()[i] = (i == n - 1) ? hi : lo + T(i) * stepv;
         return *this;
     }
     static Matrix Zero() { Matrix m; m.setZero(); return m; }

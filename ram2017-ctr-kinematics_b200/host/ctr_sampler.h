@@ -99,8 +99,10 @@ CTR_SAMPLER_HD double scale_gamma(double u, double gamma, int lut)
     const int    i0 = (int)floor(x);
     const int    i1 = (int)ceil(x);
     const double md = x - (double)i0;
-    const double f0 = pow((double)i0 / (double)(lut - 1), gamma);
-    const double f1 = pow((double)i1 / (double)(lut - 1), gamma);
+    // table nodes as Eigen 3.3's setLinSpaced(n, 0, 1) produces them: i * (1/(n-1)), the last one exactly 1
+    const double st = s_div(1.0, (double)(lut - 1));
+    const double f0 = pow(i0 == lut - 1 ? 1.0 : s_mul((double)i0, st), gamma);
+    const double f1 = pow(i1 == lut - 1 ? 1.0 : s_mul((double)i1, st), gamma);
     return f1 * md + f0 * (1.0 - md);
 }
 

@@ -224,3 +224,40 @@ def test_mt19937_joint_draws(ctrfk, robots, refs):
             scale[s] = d.sec[i].length
         want = (u[:50 * ref.njoints].reshape(50, ref.njoints)) * scale
         assert np.array_equal(got, want)
+
+
+def sampler_u01(seed, first, B, njv):
+    """numpy replica of ctrk::sampler_u01 (host/ctr_sampler.h), checked in tests/test_host.py."""
+    def splitmix64(z):
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        i = (np.arange(B, dtype=np.uint64) + np.uint64(first))[:, None]
+        j = np.arange(njv, dtype=np.uint64)[None, :]
+        b = splitmix64(splitmix64(np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * i) + j)
+    return (b >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+
+
+def test_scale_policies_against_the_reference_classes(ctrfk, robots, refs):
+    """ctr_fk_sample_joints_scaled_host against the reference's own GammaCorrection / ProportionalScale
+    (transrotscale.h), fed with the very uniform variates the counter-based sampler draws."""
+    name = "ctr_sec3_tub4.xml"
+    d, ref = robots[name], refs[name]
+    B, seed = 3000, 9
+    u = sampler_u01(seed, 0, B, d.njoints)
+    phi = util.phi_indices(d)
+    lens = np.array([d.sec[s].length for s in range(d.nsections)])
+    for lut in (0, 16, 64, 256, 1024):
+        got = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_GAMMA, p0=2.5, lut_size=lut)
+        want = lens * ref_lib.gamma_scale(lut, 2.5, u[:, phi])          # section_i.h:341: m_Length * scaleTrans(u)
+        assert np.array_equal(got[:, phi], want), lut
+    # ProportionalScale carries its goal from one configuration to the next (the last-section draw, :286-288);
+    # the first goal comes from std::rand() in the reference and from an extra sampler slot here, so configuration 0
+    # is compared after handing the reference's first goal to the formula, every later one directly
+    p0, p1 = 0.3, 0.6
+    got = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_PROPORTIONAL, p0=p0, p1=p1)
+    want, first_goal = ref_lib.proportional_scale(ref, p0, p1, u[:, phi])
+    assert p0 <= first_goal <= p1
+    assert np.array_equal(got[1:, phi], lens * want[1:])
