@@ -432,53 +432,82 @@ static void jac_column(const double* lo, const double* hi, double dq, double* co
     col[5] = ((mprod[3 * 0 + 1] - mprod[3 * 1 + 0]) * 0.5) / dq;      /* (M(1,0)-M(0,1))/2, :55 */
 }
 
-int ctr_oracle_jacobian(const ctr_robot_desc* desc, const double* jv, int32_t nsamples,
-                        double fd_trans, double fd_rot, double* jac, double* tip12)
+/* analytic column 0, robot_i.h:956-959 (:1064-1072 for the sample): axis = z column of the entry rotation */
+static void jac_column0(const model_t* m, const double* frame, double* jac)
 {
-    int rc = check_args(desc, jv, CTR_FK_MODE_NSAMPLE, 0.0, nsamples);
+    const double* z = &m->ini[6];
+    double r[3] = { frame[9] - m->ini[9], frame[10] - m->ini[10], frame[11] - m->ini[11] };
+    jac[0] = z[1] * r[2] - z[2] * r[1];
+    jac[1] = z[2] * r[0] - z[0] * r[2];
+    jac[2] = z[0] * r[1] - z[1] * r[0];
+    jac[3] = z[0]; jac[4] = z[1]; jac[5] = z[2];
+}
+
+/* All calcJacobian forms of the reference:
+ *   mode NSAMPLE, i_sample < 0  : calcKinematic(JV, N) + calcJacobian(JV, Tip, N, ..)            robot_i.h:917-960
+ *   mode STEP,    i_sample < 0  : calcJacobian(JV, ArcLengthStep, ..) = calcKinematic(JV, step), then the
+ *                                 form above with N = m_Samples of that call                     :901-907
+ *   mode NSAMPLE, i_sample >= 0 : calcJacobian(JV, N, .., iSample, JTip, JiSample)               :908-915, :1012-1072
+ * The perturbed solves are always NSamples-mode solves (:935, :951), also in the step form.       */
+int ctr_oracle_jacobian_ex(const ctr_robot_desc* desc, const double* jv, int mode, double step, int32_t nsamples,
+                           int32_t i_sample, double fd_trans, double fd_rot, double* jac_tip, double* jac_sample,
+                           double* tip12, double* sample12, int32_t* n_out)
+{
+    int rc = check_args(desc, jv, mode, step, nsamples);
     if (rc) return rc;
-    if (!jac) return CTR_FK_E_NULL;
+    if (!jac_tip || (i_sample >= 0 && !jac_sample)) return CTR_FK_E_NULL;
     model_t m;
     if ((rc = build_model(desc, &m))) return rc;
     scratch_t w;
     if ((rc = scratch_alloc(&w, m.maxs))) { scratch_free(&w); return rc; }
     const int njv = 1 + m.S + m.T;
-    double q[CTR_FK_MAX_JV], tip[12], pert[12];
+    double q[CTR_FK_MAX_JV], tip[12], pert[12], smp[12];
+    int32_t n0 = 0;
     memcpy(q, jv, sizeof(double) * (size_t)njv);
-    int st = fk_one(&m, &w, q, CTR_FK_MODE_NSAMPLE, 0.0, nsamples, tip, NULL, NULL, NULL);
+    int st = fk_one(&m, &w, q, mode, step, nsamples, tip, &n0, NULL, NULL);
     if (st) { scratch_free(&w); return st; }
-    memset(jac, 0, sizeof(double) * 6 * (size_t)njv);                 /* column 2 = 0, :928 */
-    for (int s = 0; s < m.S; ++s)                                     /* tubes 1..T-1, :929-939 */
+    if (i_sample >= n0) { scratch_free(&w); return CTR_FK_E_ARG; }     /* the reference would read a stale frame */
+    const int32_t N = (mode == CTR_FK_MODE_STEP) ? n0 : nsamples;        /* m_Samples, :906 */
+    if (i_sample >= 0) memcpy(smp, &w.frames[12 * i_sample], sizeof smp);
+    memset(jac_tip, 0, sizeof(double) * 6 * (size_t)njv);                /* column 2 = 0, :928 */
+    if (i_sample >= 0) memset(jac_sample, 0, sizeof(double) * 6 * (size_t)njv);
+    for (int s = 0; s < m.S; ++s)                                        /* tubes 1..T-1, :929-939 */
         for (int k = 0; k < m.n[s]; ++k) {
             int t = m.t0[s] + k;
             if (t == 0) continue;
             int j = 2 + s + t;
             double keep = q[j];
             q[j] = keep + fd_rot;
-            fk_one(&m, &w, q, CTR_FK_MODE_NSAMPLE, 0.0, nsamples, pert, NULL, NULL, NULL);
-            jac_column(tip, pert, fd_rot, jac + 6 * j);
+            fk_one(&m, &w, q, CTR_FK_MODE_NSAMPLE, 0.0, N, pert, NULL, NULL, NULL);
+            jac_column(tip, pert, fd_rot, jac_tip + 6 * j);
+            if (i_sample >= 0) jac_column(smp, &w.frames[12 * i_sample], fd_rot, jac_sample + 6 * j);
             q[j] = keep;
         }
-    for (int s = 0; s < m.S; ++s) {                                   /* sections, :941-954 */
+    for (int s = 0; s < m.S; ++s) {                                      /* sections, :941-954 */
         int j = m.t0[s] + s + 1;
         double keep = q[j], dq;
         q[j] = keep + fd_trans;
         if (q[j] >= m.len[s]) { q[j] = keep - fd_trans; dq = -fd_trans; }
         else dq = fd_trans;
-        fk_one(&m, &w, q, CTR_FK_MODE_NSAMPLE, 0.0, nsamples, pert, NULL, NULL, NULL);
-        jac_column(tip, pert, dq, jac + 6 * j);
+        fk_one(&m, &w, q, CTR_FK_MODE_NSAMPLE, 0.0, N, pert, NULL, NULL, NULL);
+        jac_column(tip, pert, dq, jac_tip + 6 * j);
+        if (i_sample >= 0) jac_column(smp, &w.frames[12 * i_sample], dq, jac_sample + 6 * j);
         q[j] = keep;
     }
-    /* analytic column 0, :956-959: axis = z column of the entry rotation */
-    const double* z = &m.ini[6];
-    double r[3] = { tip[9] - m.ini[9], tip[10] - m.ini[10], tip[11] - m.ini[11] };
-    jac[0] = z[1] * r[2] - z[2] * r[1];
-    jac[1] = z[2] * r[0] - z[0] * r[2];
-    jac[2] = z[0] * r[1] - z[1] * r[0];
-    jac[3] = z[0]; jac[4] = z[1]; jac[5] = z[2];
+    jac_column0(&m, tip, jac_tip);
+    if (i_sample >= 0) jac_column0(&m, smp, jac_sample);
     if (tip12) memcpy(tip12, tip, sizeof tip);
+    if (sample12 && i_sample >= 0) memcpy(sample12, smp, sizeof smp);
+    if (n_out) *n_out = n0;
     scratch_free(&w);
     return 0;
+}
+
+int ctr_oracle_jacobian(const ctr_robot_desc* desc, const double* jv, int32_t nsamples,
+                        double fd_trans, double fd_rot, double* jac, double* tip12)
+{
+    return ctr_oracle_jacobian_ex(desc, jv, CTR_FK_MODE_NSAMPLE, 0.0, nsamples, -1, fd_trans, fd_rot, jac, NULL,
+                                  tip12, NULL, NULL);
 }
 
 /* ---- calcStability: robot_i.h:756-818 ----------------------------------------------------- */

@@ -49,6 +49,13 @@ int ctr_oracle_fk_batch(const ctr_robot_desc* desc, const double* jv, int64_t B,
 int ctr_oracle_jacobian(const ctr_robot_desc* desc, const double* jv, int32_t nsamples,
                         double fd_trans, double fd_rot, double* jac, double* tip12);
 
+/* Every calcJacobian form (robot_i.h:901-1072): mode STEP = the ArcLengthStep form (:901-907: base pose from
+ * calcKinematic(JV, step), perturbed solves in NSamples mode with N = m_Samples); i_sample >= 0 = the form that
+ * also returns the Jacobian of sample i's frame (:908-915, :1012-1072).  jac_*: 6 x n_jv column-major. */
+int ctr_oracle_jacobian_ex(const ctr_robot_desc* desc, const double* jv, int mode, double step, int32_t nsamples,
+                           int32_t i_sample, double fd_trans, double fd_rot, double* jac_tip, double* jac_sample,
+                           double* tip12, double* sample12, int32_t* n_out);
+
 /* calcStability, robot_i.h:756-818.  Returns 1 stable, 0 unstable, <0 error. */
 int ctr_oracle_stability(const ctr_robot_desc* desc, const double* jv, double angle_step,
                          double arc_step);

@@ -29,6 +29,9 @@ def load():
                                             _P, _P, _P, _P, _P, _P, _P]
         lib.ctr_oracle_jacobian.restype = C.c_int
         lib.ctr_oracle_jacobian.argtypes = [_P, _P, C.c_int32, C.c_double, C.c_double, _P, _P]
+        lib.ctr_oracle_jacobian_ex.restype = C.c_int
+        lib.ctr_oracle_jacobian_ex.argtypes = [_P, _P, C.c_int, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                               _P, _P, _P, _P, _P]
         lib.ctr_oracle_stability.restype = C.c_int
         lib.ctr_oracle_stability.argtypes = [_P, _P, C.c_double, C.c_double]
         lib.ctr_oracle_degree_stability.restype = C.c_int
@@ -92,6 +95,18 @@ def jacobian(desc, jv, nsamples, fd_trans, fd_rot):
     if rc != 0:
         raise RuntimeError("oracle jacobian error %d" % rc)
     return jac, tip
+
+
+def jacobian_ex(desc, jv, mode, step=0.0, nsamples=0, i_sample=-1, fd_trans=1e-5, fd_rot=1e-4):
+    """All calcJacobian forms; returns dict(jac, jac_sample, tip, sample, n)."""
+    jv = np.ascontiguousarray(jv, dtype=np.float64)
+    njv = jv.shape[0]
+    jac = np.zeros((njv, 6)); js = np.zeros((njv, 6)); tip = np.zeros(12); smp = np.zeros(12); n = C.c_int32(0)
+    rc = load().ctr_oracle_jacobian_ex(C.addressof(desc), jv.ctypes.data, mode, step, nsamples, i_sample, fd_trans, fd_rot,
+                                       jac.ctypes.data, js.ctypes.data, tip.ctypes.data, smp.ctypes.data, C.addressof(n))
+    if rc != 0:
+        raise RuntimeError("oracle jacobian_ex error %d" % rc)
+    return dict(jac=jac, jac_sample=js if i_sample >= 0 else None, tip=tip, sample=smp if i_sample >= 0 else None, n=n.value)
 
 
 def stability(desc, jv, angle_step, arc_step):

@@ -231,3 +231,46 @@ int ctr_ref_proportional_scale(void* h, double p0, double p1, const double* u, i
 }
 
 }  // extern "C"
+
+// ---- the other calcJacobian forms ----------------------------------------------------------------------
+extern "C" {
+
+// calcJacobian(JV, ArcLengthStep, dTrans, dRot, J) (ctr_robot.h:121, robot_i.h:901-907)
+int ctr_ref_jacobian_step(void* h, const double* jv, double step, double fd_trans, double fd_rot, double* jac,
+                          double* tip12, int32_t* n_out)
+{
+    RefRobot* r = static_cast<RefRobot*>(h);
+    if (!r || !r->init()) return -1;
+    const int nj = int(r->getNJointValues());
+    RefRobot::VectorJ q(nj, 1);
+    std::memcpy(q.data(), jv, sizeof(double) * size_t(nj));
+    if (tip12 || n_out) {       // the base pose of the step form, from a call of its own (the Jacobian call redoes it)
+        RefRobot::Transform t = r->calcKinematic(q, step);
+        if (tip12) t.getData(tip12, Erl::ColMajor);
+        if (n_out) *n_out = int32_t(r->getNSamples());
+    }
+    RefRobot::MatJacobian J(6, nj);
+    J.setZero();
+    r->calcJacobian(q, step, fd_trans, fd_rot, J);
+    std::memcpy(jac, J.data(), sizeof(double) * 6 * size_t(nj));
+    return 0;
+}
+
+// calcJacobian(JV, NSamples, dTrans, dRot, iSample, JTip, JiSample) (ctr_robot.h:122, robot_i.h:908-915, :1012-1072)
+int ctr_ref_jacobian_sample(void* h, const double* jv, int32_t nsamples, int32_t i_sample, double fd_trans, double fd_rot,
+                            double* jac_tip, double* jac_sample)
+{
+    RefRobot* r = static_cast<RefRobot*>(h);
+    if (!r || !r->init()) return -1;
+    const int nj = int(r->getNJointValues());
+    RefRobot::VectorJ q(nj, 1);
+    std::memcpy(q.data(), jv, sizeof(double) * size_t(nj));
+    RefRobot::MatJacobian J(6, nj), K(6, nj);
+    J.setZero(); K.setZero();
+    r->calcJacobian(q, size_t(nsamples), fd_trans, fd_rot, size_t(i_sample), J, K);
+    std::memcpy(jac_tip, J.data(), sizeof(double) * 6 * size_t(nj));
+    std::memcpy(jac_sample, K.data(), sizeof(double) * 6 * size_t(nj));
+    return 0;
+}
+
+}  // extern "C"

@@ -49,6 +49,8 @@ def load():
         lib.ctr_ref_degree_stability.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P]
         lib.ctr_ref_random_joints.argtypes = [_P, C.c_int64, _P]
         lib.ctr_ref_max_threads.restype = C.c_int
+        lib.ctr_ref_jacobian_step.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P]
+        lib.ctr_ref_jacobian_sample.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P]
         lib.ctr_ref_gamma_scale.argtypes = [C.c_int, C.c_double, _P, C.c_int64, _P]
         lib.ctr_ref_proportional_scale.argtypes = [_P, C.c_double, C.c_double, _P, C.c_int64, _P, _P]
         _lib = lib
@@ -114,6 +116,24 @@ class RefRobot:
         if rc != 0:
             raise RuntimeError("reference jacobian error %d" % rc)
         return jac, tip
+
+    def jacobian_step(self, jv, step, fd_trans, fd_rot):
+        """calcJacobian(JV, ArcLengthStep, ...) (robot_i.h:901-907); returns (jac, base tip, m_Samples)."""
+        jv = np.ascontiguousarray(jv, dtype=np.float64)
+        jac = np.zeros((self.njoints, 6)); tip = np.zeros(12); n = C.c_int32(0)
+        rc = load().ctr_ref_jacobian_step(self.h, jv.ctypes.data, step, fd_trans, fd_rot, jac.ctypes.data, tip.ctypes.data, C.addressof(n))
+        if rc != 0:
+            raise RuntimeError("reference jacobian_step error %d" % rc)
+        return jac, tip, n.value
+
+    def jacobian_sample(self, jv, nsamples, i_sample, fd_trans, fd_rot):
+        """calcJacobian(JV, NSamples, ..., iSample, JTip, JiSample) (robot_i.h:908-915, :1012-1072)."""
+        jv = np.ascontiguousarray(jv, dtype=np.float64)
+        jac = np.zeros((self.njoints, 6)); js = np.zeros((self.njoints, 6))
+        rc = load().ctr_ref_jacobian_sample(self.h, jv.ctypes.data, nsamples, i_sample, fd_trans, fd_rot, jac.ctypes.data, js.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("reference jacobian_sample error %d" % rc)
+        return jac, js
 
     def stability(self, jv, angle_step, arc_step):
         jv = np.ascontiguousarray(jv, dtype=np.float64)

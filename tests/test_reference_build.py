@@ -261,3 +261,23 @@ def test_scale_policies_against_the_reference_classes(ctrfk, robots, refs):
     want, first_goal = ref_lib.proportional_scale(ref, p0, p1, u[:, phi])
     assert p0 <= first_goal <= p1
     assert np.array_equal(got[1:, phi], lens * want[1:])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_jacobian_other_forms_bit_equal(ctrfk, oracle, robots, refs, name):
+    """The ArcLengthStep form (robot_i.h:901-907: base pose from step mode, perturbed solves in NSamples mode with
+    N = m_Samples — the reference mixes the two discretisations, reproduced) and the iSample form (:908-915,
+    :1012-1072: Jacobian of an intermediate sample's frame next to the tip's)."""
+    d, ref = robots[name], refs[name]
+    jv = ctrfk.sample_joints_host(d, 41, 0, 24)
+    jv[0, 1] = d.sec[0].length
+    for q in jv:
+        o = oracle.jacobian_ex(d, q, ctrfk.MODE_STEP, step=d.max_length / 200.0)
+        jr, tr, nr = ref.jacobian_step(q, d.max_length / 200.0, 1e-5, 1e-4)
+        assert o["n"] == nr and np.array_equal(o["tip"], tr) and np.array_equal(o["jac"], jr)
+        for i_sample in (0, 37, 99):
+            o = oracle.jacobian_ex(d, q, ctrfk.MODE_NSAMPLE, nsamples=100, i_sample=i_sample)
+            jt, js = ref.jacobian_sample(q, 100, i_sample, 1e-5, 1e-4)
+            assert np.array_equal(o["jac"], jt) and np.array_equal(o["jac_sample"], js)
+        # the tip is the last sample
+        assert np.array_equal(o["jac"], o["jac_sample"])
