@@ -172,6 +172,31 @@ int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t 
 int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples,
                          double fd_trans, double fd_rot, double* jac, double* tip);
 
+/* Every calcJacobian form of the reference (ctr_robot.h:121-126, robot_i.h:901-1072), DEVICE pointers:
+ *   mode = CTR_FK_MODE_NSAMPLE, i_sample < 0   calcKinematic(JV, N) + calcJacobian(JV, Tip, N, ..)   (:917-960)
+ *   mode = CTR_FK_MODE_STEP,    i_sample < 0   calcJacobian(JV, ArcLengthStep, ..) (:901-907): the base pose comes
+ *                                              from calcKinematic(JV, step), the perturbed solves run in NSamples
+ *                                              mode with N = m_Samples of that call — the reference differences two
+ *                                              discretisations here; reproduced, not repaired
+ *   i_sample >= 0                              calcJacobian(JV, N, .., iSample, JTip, JiSample) (:908-915,
+ *                                              :1012-1072): jac_sample[B][n_jv][6] receives the Jacobian of the
+ *                                              frame of sample i_sample, `sample` (nullable) that frame
+ *   flags & CTR_FK_FLAG_JAC_GIVEN_POSES        calcJacobian(JV, TTip, N, ..) (:917) and (JV, TTip, TiSample, N, ..,
+ *                                              iSample, ..) (:1012): `tip` (and `sample`) are INPUTS, the base
+ *                                              poses the caller already has; no base solve is run
+ * tip, sample [B][12]; n_out [B] = m_Samples of the base solve; all three nullable (unless given).  A
+ * configuration whose i_sample is not below its sample count gets NaN in jac_sample/sample (the reference would
+ * read a stale frame). */
+#define CTR_FK_FLAG_JAC_GIVEN_POSES 0x100u
+int ctr_fk_jacobian_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                             int32_t nsamples, int32_t i_sample, double fd_trans, double fd_rot,
+                             uint32_t flags, double* jac_tip, double* jac_sample, double* tip,
+                             double* sample, int32_t* n_out, void* stream);
+int ctr_fk_jacobian_host_ex(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                            int32_t nsamples, int32_t i_sample, double fd_trans, double fd_rot,
+                            uint32_t flags, double* jac_tip, double* jac_sample, double* tip,
+                            double* sample, int32_t* n_out);
+
 /* Batched calcStability / calcDegreeStability (robot_i.h:756-818, :819-899), DEVICE pointers.
  * For every tube 1..T-1 the tip angle is scanned in `angle_step` increments from 0 to its joint
  * value (or from the joint value to 2*pi when it exceeds pi); each scan point runs the tip->base

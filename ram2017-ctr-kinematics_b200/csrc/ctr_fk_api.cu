@@ -355,13 +355,21 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
     return 0;
 }
 
-int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples, double fd_trans,
-                          double fd_rot, double* jac, double* tip, void* stream)
+int ctr_fk_jacobian_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                             int32_t i_sample, double fd_trans, double fd_rot, uint32_t flags, double* jac_tip,
+                             double* jac_sample, double* tip, double* sample, int32_t* n_out, void* stream)
 {
-    int rc = check_common(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples);
+    const bool given = (flags & CTR_FK_FLAG_JAC_GIVEN_POSES) != 0;
+    if (given && B > 0 && (!tip || (i_sample >= 0 && !sample))) {
+        set_error("CTR_FK_FLAG_JAC_GIVEN_POSES needs the tip (and sample) poses as inputs");
+        return CTR_FK_E_NULL;
+    }
+    int rc = check_common(h, jv, B, mode, step, nsamples);
     if (rc) return rc;
-    if ((rc = check_align(h, jv, tip, nullptr))) return rc;
-    if (!jac && B > 0) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
+    if ((rc = check_align(h, jv, tip, sample))) return rc;
+    if (!jac_tip && B > 0) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
+    if (i_sample >= 0 && !jac_sample && B > 0) { set_error("i_sample >= 0 needs a jac_sample buffer"); return CTR_FK_E_NULL; }
+    if (i_sample >= h->rb.maxs) { set_error("i_sample %d out of range (MaxSamples %d)", i_sample, h->rb.maxs); return CTR_FK_E_ARG; }
     if (!(fd_trans != 0.0) || !(fd_rot != 0.0) || !std::isfinite(fd_trans) || !std::isfinite(fd_rot)) {
         set_error("finite-difference steps must be finite and non-zero");
         return CTR_FK_E_ARG;
@@ -370,38 +378,65 @@ int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t 
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     JacArgs a;
-    a.jv = jv; a.B = B; a.nsamples = nsamples; a.fd_trans = fd_trans; a.fd_rot = fd_rot; a.jac = jac; a.tip = tip;
+    a.jv = jv; a.B = B; a.nsamples = nsamples; a.fd_trans = fd_trans; a.fd_rot = fd_rot; a.jac = jac_tip; a.tip = tip;
+    a.mode = mode; a.step = step; a.i_sample = i_sample < 0 ? -1 : i_sample;
+    a.jac_sample = i_sample >= 0 ? jac_sample : nullptr; a.sample = i_sample >= 0 ? sample : nullptr; a.n_out = n_out;
+    a.given = given ? 1 : 0;
     cudaError_t e = launch_jacobian(h->key, h->rb, a, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail("jacobian kernel launch", e);
     return 0;
 }
 
-int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples, double fd_trans,
-                         double fd_rot, double* jac, double* tip)
+int ctr_fk_jacobian_batch(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples, double fd_trans,
+                          double fd_rot, double* jac, double* tip, void* stream)
 {
-    int rc = check_common(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples);
+    return ctr_fk_jacobian_batch_ex(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples, -1, fd_trans, fd_rot, 0, jac, nullptr,
+                                    tip, nullptr, nullptr, stream);
+}
+
+int ctr_fk_jacobian_host_ex(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                            int32_t i_sample, double fd_trans, double fd_rot, uint32_t flags, double* jac_tip,
+                            double* jac_sample, double* tip, double* sample, int32_t* n_out)
+{
+    const bool given = (flags & CTR_FK_FLAG_JAC_GIVEN_POSES) != 0;
+    if (given && B > 0 && (!tip || (i_sample >= 0 && !sample))) {
+        set_error("CTR_FK_FLAG_JAC_GIVEN_POSES needs the tip (and sample) poses as inputs");
+        return CTR_FK_E_NULL;
+    }
+    int rc = check_common(h, jv, B, mode, step, nsamples);
     if (rc) return rc;
     if (B == 0) return 0;
-    if (!jac) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
+    if (!jac_tip) { set_error("null Jacobian pointer"); return CTR_FK_E_NULL; }
+    if (i_sample >= 0 && !jac_sample) { set_error("i_sample >= 0 needs a jac_sample buffer"); return CTR_FK_E_NULL; }
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     const size_t njv = (size_t)h->njv;
     auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const bool   ws = i_sample >= 0;
     const size_t b_jv = up256(sizeof(double) * njv * (size_t)B), b_jac = up256(sizeof(double) * 6 * njv * (size_t)B),
-                 b_tip = sizeof(double) * 12 * (size_t)B;
+                 b_tip = up256(sizeof(double) * 12 * (size_t)B), b_n = up256(sizeof(int32_t) * (size_t)B);
     char* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, b_jv + b_jac + b_tip);
+    cudaError_t e = cudaMalloc((void**)&d, b_jv + 2 * b_jac + 2 * b_tip + b_n);
     if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: allocation", e);
     cudaStream_t st = h->streams[0];
-    double* d_jv = (double*)d;
-    double* d_jac = (double*)(d + b_jv);
-    double* d_tip = (double*)(d + b_jv + b_jac);
+    double*  d_jv   = (double*)d;
+    double*  d_jac  = (double*)(d + b_jv);
+    double*  d_jacs = (double*)(d + b_jv + b_jac);
+    double*  d_tip  = (double*)(d + b_jv + 2 * b_jac);
+    double*  d_smp  = (double*)(d + b_jv + 2 * b_jac + b_tip);
+    int32_t* d_n    = (int32_t*)(d + b_jv + 2 * b_jac + 2 * b_tip);
     e = cudaMemcpyAsync(d_jv, jv, sizeof(double) * njv * (size_t)B, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && given) e = cudaMemcpyAsync(d_tip, tip, sizeof(double) * 12 * (size_t)B, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && given && ws) e = cudaMemcpyAsync(d_smp, sample, sizeof(double) * 12 * (size_t)B, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        rc = ctr_fk_jacobian_batch(h, d_jv, B, nsamples, fd_trans, fd_rot, d_jac, tip ? d_tip : nullptr, st);
+        rc = ctr_fk_jacobian_batch_ex(h, d_jv, B, mode, step, nsamples, i_sample, fd_trans, fd_rot, flags, d_jac, ws ? d_jacs : nullptr,
+                                      tip ? d_tip : nullptr, (ws && sample) ? d_smp : nullptr, n_out ? d_n : nullptr, st);
         if (rc == 0) {
-            e = cudaMemcpyAsync(jac, d_jac, sizeof(double) * 6 * njv * (size_t)B, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess && tip) e = cudaMemcpyAsync(tip, d_tip, b_tip, cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(jac_tip, d_jac, sizeof(double) * 6 * njv * (size_t)B, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && ws) e = cudaMemcpyAsync(jac_sample, d_jacs, sizeof(double) * 6 * njv * (size_t)B, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && tip && !given) e = cudaMemcpyAsync(tip, d_tip, sizeof(double) * 12 * (size_t)B, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && ws && sample && !given) e = cudaMemcpyAsync(sample, d_smp, sizeof(double) * 12 * (size_t)B, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && n_out) e = cudaMemcpyAsync(n_out, d_n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st);
         }
     }
     cudaError_t es = cudaStreamSynchronize(st);
@@ -410,6 +445,13 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
     if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: copy", e);
     if (es != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: sync", es);
     return 0;
+}
+
+int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t nsamples, double fd_trans,
+                         double fd_rot, double* jac, double* tip)
+{
+    return ctr_fk_jacobian_host_ex(h, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, nsamples, -1, fd_trans, fd_rot, 0, jac, nullptr, tip,
+                                   nullptr, nullptr);
 }
 
 int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,

@@ -1340,6 +1340,163 @@ struct PendingFrameEmitter {
     }
 };
 
+// ---- finite-difference Jacobians (robot_i.h:901-1072, :41-56) ------------------------------------
+// on_sample functor: the frame product of sample ks, B = E_0 ... E_ks, accumulated next to the solver's own
+// (software-pipelined) tip product.  Its chain is independent of the sweep's, so the two overlap.
+struct SampleProduct {
+    StepConsts kc;
+    int        ks;
+    QT*        B;        // starts as the identity
+    double*    a_s;      // angle of the innermost tube at sample ks
+    CTR_HD void operator()(int k, double ux, double uy, double uz, double al) const
+    {
+        if (k > ks) return;
+        if (k == ks) *a_s = al;
+        QT E;
+        se3_step_fast_k(ux, uy, uz, kc, E.w, E.x, E.y, E.z, E.px, E.py, E.pz);
+        *B = qt_mul(E, *B);
+    }
+};
+
+// column = d(lo -> hi)/dq (robot_i.h:41-56): translation difference and the vee of (R_hi - R_lo) R_hi^T,
+// both divided by dq.
+CTR_HD void jac_column(const double* lo, const double* hi, double dq, double* col)
+{
+    double d[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) d[i] = hi[i] - lo[i];
+#define CTRK_JM(i, j) (d[i] * hi[j] + d[3 + (i)] * hi[3 + (j)] + d[6 + (i)] * hi[6 + (j)])     /* sum_k D(i,k) R_hi(j,k) */
+    col[0] = (hi[9] - lo[9]) / dq;
+    col[1] = (hi[10] - lo[10]) / dq;
+    col[2] = (hi[11] - lo[11]) / dq;
+    col[3] = ((CTRK_JM(2, 1) - CTRK_JM(1, 2)) * 0.5) / dq;
+    col[4] = ((CTRK_JM(0, 2) - CTRK_JM(2, 0)) * 0.5) / dq;
+    col[5] = ((CTRK_JM(1, 0) - CTRK_JM(0, 1)) * 0.5) / dq;
+#undef CTRK_JM
+}
+// analytic column 0 (robot_i.h:956-959, :1064-1072): rotation about the entry frame's z axis
+CTR_HD void jac_column0(const KRobot& rb, const double* f, double* jac)
+{
+    const double zx = rb.ini[6], zy = rb.ini[7], zz = rb.ini[8];
+    const double rx = f[9] - rb.ini[9], ry = f[10] - rb.ini[10], rz = f[11] - rb.ini[11];
+    jac[0] = zy * rz - zz * ry;
+    jac[1] = zz * rx - zx * rz;
+    jac[2] = zx * ry - zy * rx;
+    jac[3] = zx; jac[4] = zy; jac[5] = zz;
+}
+
+// One solve that yields the tip frame and, when ks >= 0, the frame of sample ks.
+template <class L, bool WITH_SAMPLE>
+CTR_HD void solve_tip_and_sample(const KRobot& rb, const Ctl<L>& c, int ks, double* tip, double* smp)
+{
+    if (!WITH_SAMPLE || ks < 0) {
+        solve_fast<L, true>(rb, c, tip, nullptr, NoSample{});
+        return;
+    }
+    QT     B  = qt_identity();
+    double as = 0.0;
+    SampleProduct f{make_step_consts(c.h, rb.ztol), ks, &B, &as};
+    solve_fast<L, true>(rb, c, tip, nullptr, f);
+    double sh, ch;
+    fast_sincos(0.5 * (as + c.theta), sh, ch);
+    qt_frame(rb, B, sh, ch, smp);
+}
+
+// Every calcJacobian form of the reference for one configuration (what one GPU thread runs):
+//   mode NSAMPLE, ks < 0  : calcKinematic(JV, N) + calcJacobian(JV, Tip, N, ..)              robot_i.h:917-960
+//   mode STEP,    ks < 0  : calcJacobian(JV, ArcLengthStep, ..): base pose from calcKinematic(JV, step), perturbed
+//                           solves in NSamples mode with N = m_Samples of that call (:901-907) — the reference
+//                           mixes the two discretisations; reproduced
+//   ks >= 0               : additionally the Jacobian of sample ks' frame (:908-915, :1012-1072)
+//   given                 : tip_out (and smp_out) are INPUTS — the base poses come from the caller, as in
+//                           calcJacobian(JV, TTip, N, ..) and (JV, TTip, TiSample, N, .., iSample, ..) (:917, :1012);
+//                           no base solve is run
+// jac_tip / jac_smp: [NJ][6]; tip_out / smp_out nullable [12]; returns the status of the base solve
+// (non-zero: everything NaN), n_out = m_Samples of the base solve.  ks >= m_Samples: the reference would read a
+// stale frame; the sample Jacobian and frame are NaN.
+// WITH_SAMPLE = false compiles the sample-frame path out (tip-only forms keep their register budget).
+template <class L, bool WITH_SAMPLE>
+CTR_HD int jacobian_config(const KRobot& rb, const double* q, int mode, double step, int nsamples, int ks,
+                           double fd_trans, double fd_rot, double* jac_tip, double* jac_smp, double* tip_out,
+                           double* smp_out, int32_t* n_out, bool given = false)
+{
+    constexpr int S = L::S, T = L::T, NJ = L::NJ;
+    union { long long i; double d; } qn; qn.i = 0x7ff8000000000000ll;
+    const double qnan = qn.d;
+    Ctl<L> c;
+    setup_control<L>(rb, q, mode, step, nsamples, c);
+    if (n_out) *n_out = c.status ? 0 : c.nframes;
+    if (c.status) {
+        for (int e = 0; e < NJ * 6; ++e) { jac_tip[e] = qnan; if (jac_smp) jac_smp[e] = qnan; }
+        if (tip_out && !given) for (int e = 0; e < 12; ++e) tip_out[e] = qnan;
+        if (smp_out && !given) for (int e = 0; e < 12; ++e) smp_out[e] = qnan;
+        return c.status;
+    }
+    const bool smp_ok = WITH_SAMPLE && ks >= 0 && ks < c.nframes;
+    if (!WITH_SAMPLE) { jac_smp = nullptr; smp_out = nullptr; }
+    const int  kse = smp_ok ? ks : -1;
+    const int  npert = (mode == 0) ? c.nframes : nsamples;          // m_Samples, robot_i.h:906
+    double tip0[12], smp0[12];
+    if (given) {
+        for (int e = 0; e < 12; ++e) { tip0[e] = tip_out[e]; smp0[e] = (WITH_SAMPLE && smp_ok) ? smp_out[e] : qnan; }
+    } else {
+        solve_tip_and_sample<L, WITH_SAMPLE>(rb, c, kse, tip0, smp0);
+        if (tip_out) for (int e = 0; e < 12; ++e) tip_out[e] = tip0[e];
+        if (smp_out) for (int e = 0; e < 12; ++e) smp_out[e] = smp_ok ? smp0[e] : qnan;
+    }
+
+    // column 2 (alpha of tube 0) is zero (robot_i.h:928)
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { jac_tip[2 * 6 + e] = 0.0; if (jac_smp) jac_smp[2 * 6 + e] = smp_ok ? 0.0 : qnan; }
+
+    // perturbations 0..T-2: tube angles 1..T-1 (+fd_rot); T-1..T-2+S: section extensions
+#pragma unroll 1
+    for (int p = 0; p < (T - 1) + S; ++p) {
+        int    jp = 0;
+        double dq = fd_rot;
+        if (p < T - 1) {
+            const int t = p + 1;
+            jp = 2 + L::sec_of(t) + t;
+        } else {
+            const int s = p - (T - 1);
+            jp = L::t0(s) + s + 1;
+            const double len = rb.len[s];
+            double keep = 0.0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) keep = (j == jp) ? q[j] : keep;
+            dq = (keep + fd_trans >= len) ? -fd_trans : fd_trans;       // robot_i.h:947-950
+        }
+        double qq[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) qq[j] = (j == jp) ? q[j] + dq : q[j];
+        Ctl<L> cp;
+        setup_control<L>(rb, qq, 1, 0.0, npert, cp);
+        double col[6], cols[6];
+        if (cp.status) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) col[e] = cols[e] = qnan;
+        } else {
+            double tp[12], sp[12];
+            solve_tip_and_sample<L, WITH_SAMPLE>(rb, cp, (kse >= 0 && kse < cp.nframes) ? kse : -1, tp, sp);
+            jac_column(tip0, tp, dq, col);
+            if (WITH_SAMPLE && kse >= 0 && kse < cp.nframes) jac_column(smp0, sp, dq, cols);
+            else
+#pragma unroll
+                for (int e = 0; e < 6; ++e) cols[e] = qnan;
+        }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { jac_tip[jp * 6 + e] = col[e]; if (jac_smp) jac_smp[jp * 6 + e] = cols[e]; }
+    }
+    jac_column0(rb, tip0, jac_tip);
+    if (jac_smp) {
+        if (smp_ok) jac_column0(rb, smp0, jac_smp);
+        else
+#pragma unroll
+            for (int e = 0; e < 6; ++e) jac_smp[e] = qnan;
+    }
+    return 0;
+}
+
 // robot_i.h:1286-1307: outer radius of the section covering each sample.  Writes radius[0..n)
 // with stride `stride` doubles.
 template <class L>

@@ -36,6 +36,13 @@ struct JacArgs {
     double        fd_trans, fd_rot;
     double*       jac;          // [B][NJ][6]
     double*       tip;          // [B][12] nullable
+    int           mode;         // CTR_FK_MODE_*: STEP = the ArcLengthStep form (robot_i.h:901-907)
+    double        step;
+    int           i_sample;     // >= 0: also the Jacobian of that sample's frame (robot_i.h:1012-1072)
+    double*       jac_sample;   // [B][NJ][6] nullable
+    double*       sample;       // [B][12] nullable
+    int32_t*      n_out;        // [B] nullable
+    int           given;        // tip / sample are inputs (CTR_FK_FLAG_JAC_GIVEN_POSES)
 };
 
 struct StabArgs {

@@ -14,6 +14,7 @@ REPO = os.path.dirname(HERE)
 MAX_SECTIONS = 3
 MAX_TUBES = 6
 MODE_STEP, MODE_NSAMPLE = 0, 1
+FLAG_JAC_GIVEN_POSES = 0x100
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
@@ -70,6 +71,10 @@ SYMBOLS = {
                                 _P, _P, _P, _P, _P, _P]),
     "ctr_fk_jacobian_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P, _P]),
     "ctr_fk_jacobian_host": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P]),
+    "ctr_fk_jacobian_batch_ex": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                           C.c_uint32, _P, _P, _P, _P, _P, _P]),
+    "ctr_fk_jacobian_host_ex": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                          C.c_uint32, _P, _P, _P, _P, _P]),
     "ctr_fk_stability_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "ctr_fk_stability_host": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P]),
     "ctr_fk_batch_base": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_double, C.c_int32,
@@ -213,6 +218,19 @@ class Engine:
     def jacobian_host(self, jv, B, nsamples, fd_trans, fd_rot, jac, tip=None):
         _check(load().ctr_fk_jacobian_host(self.handle, _ptr(jv), B, nsamples, fd_trans, fd_rot,
                                            _ptr(jac), _ptr(tip)))
+
+    def jacobian_ex(self, jv, B, mode, fd_trans, fd_rot, jac, step=0.0, nsamples=0, i_sample=-1, jac_sample=None,
+                    tip=None, sample=None, n_out=None, given=False, stream=None):
+        """Every calcJacobian form (include/ctr_fk.h: ctr_fk_jacobian_batch_ex), device pointers."""
+        _check(load().ctr_fk_jacobian_batch_ex(self.handle, _ptr(jv), B, mode, step, nsamples, i_sample, fd_trans, fd_rot,
+                                               FLAG_JAC_GIVEN_POSES if given else 0, _ptr(jac), _ptr(jac_sample), _ptr(tip),
+                                               _ptr(sample), _ptr(n_out), stream))
+
+    def jacobian_host_ex(self, jv, B, mode, fd_trans, fd_rot, jac, step=0.0, nsamples=0, i_sample=-1, jac_sample=None,
+                         tip=None, sample=None, n_out=None, given=False):
+        _check(load().ctr_fk_jacobian_host_ex(self.handle, _ptr(jv), B, mode, step, nsamples, i_sample, fd_trans, fd_rot,
+                                              FLAG_JAC_GIVEN_POSES if given else 0, _ptr(jac), _ptr(jac_sample), _ptr(tip),
+                                              _ptr(sample), _ptr(n_out)))
 
     def stability(self, jv, B, angle_step, arc_step, min_degree=-1.0, stable=None, degree=None, stream=None):
         _check(load().ctr_fk_stability_batch(self.handle, _ptr(jv), B, angle_step, arc_step, min_degree,

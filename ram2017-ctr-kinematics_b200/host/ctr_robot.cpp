@@ -208,6 +208,38 @@ void Robot::calcJacobian(const VectorJ& jv, const std::size_t& ns, const double&
     if (rc) std::cerr << "ERROR: calcJacobian: " << ctr_fk_last_error() << std::endl;
 }
 
+// shared tail of the other four forms: one configuration through ctr_fk_jacobian_host_ex
+void Robot::jacobianEx(const VectorJ& jv, int mode, double step, std::size_t ns, long iSample, double fdTrans, double fdRot,
+                       const Transform* tTip, const Transform* tiSample, MatJacobian& J, MatJacobian* Js, const char* who)
+{
+    J.cols = (int)getNJointValues();
+    J.data.assign((std::size_t)6 * J.cols, 0.0);
+    if (Js) { Js->cols = J.cols; Js->data.assign((std::size_t)6 * J.cols, 0.0); }
+    if (!engine_) { fool(who); return; }
+    double tip[12], smp[12];
+    if (tTip) tTip->getData(tip);
+    if (tiSample) tiSample->getData(smp);
+    int rc = ctr_fk_jacobian_host_ex(engine_, jv.data(), 1, mode, step, (int32_t)ns, (int32_t)iSample, fdTrans, fdRot,
+                                     tTip ? CTR_FK_FLAG_JAC_GIVEN_POSES : 0u, J.data.data(), Js ? Js->data.data() : nullptr,
+                                     tTip ? tip : nullptr, tiSample ? smp : nullptr, nullptr);
+    if (rc) std::cerr << "ERROR: " << who << ": " << ctr_fk_last_error() << std::endl;
+}
+
+void Robot::calcJacobian(const VectorJ& jv, const double& step, const double& fdTrans, const double& fdRot, MatJacobian& J)
+{ jacobianEx(jv, CTR_FK_MODE_STEP, step, 1, -1, fdTrans, fdRot, nullptr, nullptr, J, nullptr, __func__); }
+
+void Robot::calcJacobian(const VectorJ& jv, const std::size_t& ns, const double& fdTrans, const double& fdRot,
+                         const std::size_t& iSample, MatJacobian& J, MatJacobian& Js)
+{ jacobianEx(jv, CTR_FK_MODE_NSAMPLE, 0.0, ns, (long)iSample, fdTrans, fdRot, nullptr, nullptr, J, &Js, __func__); }
+
+void Robot::calcJacobian(const VectorJ& jv, const Transform& tTip, const std::size_t& ns, const double& fdTrans,
+                         const double& fdRot, MatJacobian& J)
+{ jacobianEx(jv, CTR_FK_MODE_NSAMPLE, 0.0, ns, -1, fdTrans, fdRot, &tTip, nullptr, J, nullptr, __func__); }
+
+void Robot::calcJacobian(const VectorJ& jv, const Transform& tTip, const Transform& tiSample, const std::size_t& ns,
+                         const double& fdTrans, const double& fdRot, const std::size_t& iSample, MatJacobian& J, MatJacobian& Js)
+{ jacobianEx(jv, CTR_FK_MODE_NSAMPLE, 0.0, ns, (long)iSample, fdTrans, fdRot, &tTip, &tiSample, J, &Js, __func__); }
+
 bool Robot::calcStability(const VectorJ& jv, const double& angleStep, const double& arcStep)
 {
     if (!engine_) { fool(__func__); return false; }                     // ctr_robot.cpp null-robot branch

@@ -84,7 +84,17 @@ public:
                                const double& minDegreeStability = -1.);
     bool   getStable() const noexcept { return stable_; }
 
-    // ctr_robot.h:122 (NSamples form, tip only)
+    // ctr_robot.h:121-126: the four calcJacobian forms of the reference ...
+    void calcJacobian(const VectorJ& jv, const double& arcLengthStep, const double& fdTrans, const double& fdRot,
+                      MatJacobian& jacobianTip);
+    void calcJacobian(const VectorJ& jv, const std::size_t& nSamples, const double& fdTrans, const double& fdRot,
+                      const std::size_t& iSample, MatJacobian& jacobianTip, MatJacobian& jacobianiSample);
+    void calcJacobian(const VectorJ& jv, const Transform& tTip, const std::size_t& nSamples, const double& fdTrans,
+                      const double& fdRot, MatJacobian& jacobianTip);
+    void calcJacobian(const VectorJ& jv, const Transform& tTip, const Transform& tiSample, const std::size_t& nSamples,
+                      const double& fdTrans, const double& fdRot, const std::size_t& iSample, MatJacobian& jacobianTip,
+                      MatJacobian& jacobianiSample);
+    // ... and the NSamples form with the tip only (calcKinematic(JV, N) + the third form; not in the reference's façade)
     void calcJacobian(const VectorJ& jv, const std::size_t& nSamples, const double& fdTrans, const double& fdRot,
                       MatJacobian& jacobianTip);
 
@@ -114,6 +124,8 @@ private:
     void build(int device);
     void destroy();
     Transform solve_single(const double* jv, int mode, double step, std::size_t ns, double* stepReturn);
+    void jacobianEx(const VectorJ& jv, int mode, double step, std::size_t ns, long iSample, double fdTrans, double fdRot,
+                    const Transform* tTip, const Transform* tiSample, MatJacobian& J, MatJacobian* Js, const char* who);
 
     ctr_robot_desc desc_;
     ctr_fk_handle  engine_;

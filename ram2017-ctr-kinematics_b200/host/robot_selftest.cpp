@@ -97,6 +97,22 @@ int main(int argc, char** argv)
     const ctr_robot_desc& d = robot.descriptor();
     CHECK(J(3, 0) == d.init_trafo[6] && J(4, 0) == d.init_trafo[7] && J(5, 0) == d.init_trafo[8]);
 
+    // the reference's other calcJacobian forms (ctr_robot.h:121-126)
+    {
+        MatJacobian Jt, Js, Jg, Jgs, Jstep;
+        robot.calcJacobian(jv, std::size_t(128), 1e-5, 1e-4, std::size_t(127), Jt, Js);      // iSample = tip sample
+        for (int c = 0; c < 6; ++c) for (int r = 0; r < 6; ++r) { CHECK(Jt(r, c) == J(r, c)); CHECK(Js(r, c) == Jt(r, c) || std::fabs(Js(r, c) - Jt(r, c)) < 1e-6); }
+        robot.calcJacobian(jv, std::size_t(128), 1e-5, 1e-4, std::size_t(40), Jt, Js);
+        CHECK(Js(3, 0) == d.init_trafo[6] && Js(0, 2) == 0.0 && std::fabs(Js(0, 1) - Jt(0, 1)) > 1e-9);
+        Transform tip = robot.calcKinematic(jv, std::size_t(128));
+        Transform smp = robot.getTransformSample(40);
+        robot.calcJacobian(jv, tip, std::size_t(128), 1e-5, 1e-4, Jg);                       // base pose handed in
+        robot.calcJacobian(jv, tip, smp, std::size_t(128), 1e-5, 1e-4, std::size_t(40), Jg, Jgs);
+        for (int c = 0; c < 6; ++c) for (int r = 0; r < 6; ++r) { CHECK(std::fabs(Jg(r, c) - Jt(r, c)) < 1e-6); CHECK(std::fabs(Jgs(r, c) - Js(r, c)) < 1e-6); }
+        robot.calcJacobian(jv, robot.getMaxLength() / 256.0, 1e-5, 1e-4, Jstep);             // ArcLengthStep form
+        CHECK(Jstep.cols == 6 && Jstep(3, 0) == d.init_trafo[6] && Jstep(2, 2) == 0.0);
+    }
+
     // stability: a barely inserted robot is stable
     VectorJ qs = {0.0, 0.005, 0.0, 0.5, 0.005, 0.7};
     CHECK(robot.calcStability(qs, 0.05, robot.getMaxLength() / 256.0) && robot.getStable());

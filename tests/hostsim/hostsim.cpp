@@ -202,6 +202,37 @@ extern "C" int hostsim_emit_full(const ctr_robot_desc* d, const double* jv, int6
     return 0;
 }
 
+// jacobian_config (what one GPU thread of fk_jacobian_kernel runs), B configurations
+namespace {
+template <class L>
+void jacobian_all(const KRobot& rb, const double* jv, int64_t B, int mode, double step, int ns, int ks, double fdt, double fdr,
+                  double* jac, double* jacs, double* tip, double* smp, int32_t* n_out, bool given)
+{
+    for (int64_t i = 0; i < B; ++i)
+        if (ks >= 0) jacobian_config<L, true>(rb, jv + i * L::NJ, mode, step, ns, ks, fdt, fdr, jac + i * L::NJ * 6,
+                           jacs ? jacs + i * L::NJ * 6 : nullptr, tip ? tip + 12 * i : nullptr, smp ? smp + 12 * i : nullptr,
+                           n_out ? n_out + i : nullptr, given);
+        else jacobian_config<L, false>(rb, jv + i * L::NJ, mode, step, ns, ks, fdt, fdr, jac + i * L::NJ * 6,
+                           jacs ? jacs + i * L::NJ * 6 : nullptr, tip ? tip + 12 * i : nullptr, smp ? smp + 12 * i : nullptr,
+                           n_out ? n_out + i : nullptr, given);
+}
+}  // namespace
+
+extern "C" int hostsim_jacobian(const ctr_robot_desc* d, const double* jv, int64_t B, int mode, double step, int ns, int ks,
+                                double fdt, double fdr, double* jac, double* jacs, double* tip, double* smp, int32_t* n_out, int given)
+{
+    KRobot rb;
+    int rc = make_krobot(d, &rb);
+    if (rc) return rc;
+    switch (layout_key(d)) {
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: jacobian_all<Lay<S, A, Bq, C>>(rb, jv, B, mode, step, ns, ks, fdt, fdr, jac, jacs, tip, smp, n_out, given != 0); break;
+        CTRK_FOR_EACH_LAYOUT(X)
+#undef X
+        default: return CTR_FK_E_DESC;
+    }
+    return 0;
+}
+
 #ifdef CTRK_COUNT_COLD   // analysis build (tools/tier_shares.py): how many sweep iterations left the hot form
 extern "C" void hostsim_tier_counters(long long* out3, int reset)
 {

@@ -333,6 +333,52 @@ def test_jacobian_parity(ctrfk, oracle, robots, engines, name):
         assert np.all(jac[i][2] == 0.0)
 
 
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_jacobian_other_forms(ctrfk, oracle, robots, engines, name):
+    """ctr_fk_jacobian_batch_ex: the ArcLengthStep form (robot_i.h:901-907), the iSample form (:1012-1072) and the
+    forms that take the base poses from the caller, against the oracle (itself bit-equal to the reference build)."""
+    d, eng = robots[name], engines[name]
+    B = 150
+    jv_np = ctrfk.sample_joints_host(d, 23, 0, B)
+    jv_np[0, 1] = d.sec[0].length - 1e-7
+    jv_np[3, 1] = -0.2                                            # invalid -> NaN
+    jv = torch.from_numpy(jv_np).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    nj = d.njoints
+    for mode, kw, ks in ((0, dict(step=d.max_length / 200.0), -1), (1, dict(nsamples=100), 37), (1, dict(nsamples=100), 0)):
+        jac = torch.zeros(B, nj, 6, dtype=torch.float64, device="cuda"); jacs = torch.zeros_like(jac)
+        tip = torch.zeros(B, 12, dtype=torch.float64, device="cuda"); smp = torch.zeros_like(tip)
+        n = torch.zeros(B, dtype=torch.int32, device="cuda")
+        before = ctrfk.launch_count()
+        eng.jacobian_ex(jv, B, mode, 1e-5, 1e-4, jac, i_sample=ks, jac_sample=jacs if ks >= 0 else None, tip=tip,
+                        sample=smp if ks >= 0 else None, n_out=n, stream=st, **kw)
+        torch.cuda.synchronize()
+        assert ctrfk.launch_count() > before
+        J, Js, T, Sm, N = (x.cpu().numpy() for x in (jac, jacs, tip, smp, n))
+        assert np.isnan(J[3]).all() and np.isnan(T[3]).all() and N[3] == 0
+        for i in list(range(0, B, 9)) + [1]:
+            if i == 3:
+                continue
+            o = oracle.jacobian_ex(d, jv_np[i], mode, i_sample=ks, **kw)
+            assert N[i] == o["n"]
+            dp, ang = util.pose_errors(o["tip"][None], T[i][None])
+            assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+            assert np.abs(o["jac"] - J[i]).max() < 1e-6
+            if ks >= 0:
+                dp, ang = util.pose_errors(o["sample"][None], Sm[i][None])
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+                assert np.abs(o["jac_sample"] - Js[i]).max() < 1e-6
+        if mode == 1:       # base poses handed in (robot_i.h:917, :1012): identical columns, through the host entry
+            J2 = np.zeros((B, nj, 6)); Js2 = np.zeros((B, nj, 6))
+            eng.jacobian_host_ex(jv_np, B, 1, 1e-5, 1e-4, J2, nsamples=100, i_sample=ks, jac_sample=Js2, tip=T, sample=Sm, given=True)
+            ok = np.arange(B) != 3
+            assert np.array_equal(J2[ok], J[ok]) and np.array_equal(Js2[ok], Js[ok])
+    # the step form reproduces the reference's mixing of two discretisations: its columns differ from the NSamples
+    # form at the same sample count by O(h)/dq
+    with pytest.raises(ctrfk.CtrFkError):
+        eng.jacobian_ex(jv, B, 1, 1e-5, 1e-4, jac, nsamples=100, i_sample=5, stream=st)       # no jac_sample buffer
+
+
 # ---- full-size, size-independent properties (BASELINE.json config 2: 1M configurations) --------
 
 def rz_batch(theta):

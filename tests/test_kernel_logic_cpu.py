@@ -213,3 +213,42 @@ def test_frame_emission_matches_oracle(ctrfk, oracle, hostsim, robots, name):
                 dp, ang = util.pose_errors(o["backbone"][i, :nf], got[i, :nf])
                 worst_p = max(worst_p, dp.max()); worst_r = max(worst_r, ang.max())
             assert worst_p < 2e-10 and worst_r < 1e-11, (mode, step, ns, worst_p, worst_r)
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_jacobian_config_all_forms(ctrfk, oracle, hostsim, robots, name):
+    """jacobian_config (the per-thread routine of fk_jacobian_kernel) for every calcJacobian form of the
+    reference: NSamples form, ArcLengthStep form (robot_i.h:901-907), iSample form (:1012-1072)."""
+    import ctypes as C
+    d = robots[name]
+    B = 12
+    jv = ctrfk.sample_joints_host(d, 17, 0, B)
+    jv[0, 1] = d.sec[0].length
+    hostsim.hostsim_jacobian.restype = C.c_int
+    hostsim.hostsim_jacobian.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                                         C.c_double] + [C.c_void_p] * 5 + [C.c_int]
+    for mode, kw, ks in ((1, dict(nsamples=100), -1), (0, dict(step=d.max_length / 200.0), -1), (1, dict(nsamples=100), 37),
+                         (1, dict(nsamples=100), 0), (1, dict(nsamples=100), 99)):
+        jac = np.zeros((B, d.njoints, 6)); jacs = np.zeros((B, d.njoints, 6)); tip = np.zeros((B, 12)); smp = np.zeros((B, 12))
+        n = np.zeros(B, np.int32)
+        rc = hostsim.hostsim_jacobian(C.addressof(d), jv.ctypes.data, B, mode, kw.get("step", 0.0), kw.get("nsamples", 0), ks, 1e-5,
+                                      1e-4, jac.ctypes.data, jacs.ctypes.data if ks >= 0 else None, tip.ctypes.data,
+                                      smp.ctypes.data if ks >= 0 else None, n.ctypes.data, 0)
+        assert rc == 0
+        if mode == 1:       # the forms that take the base poses from the caller (robot_i.h:917, :1012): same columns
+            jac2 = np.zeros_like(jac); jacs2 = np.zeros_like(jacs)
+            rc = hostsim.hostsim_jacobian(C.addressof(d), jv.ctypes.data, B, mode, 0.0, kw["nsamples"], ks, 1e-5, 1e-4,
+                                          jac2.ctypes.data, jacs2.ctypes.data if ks >= 0 else None, tip.ctypes.data,
+                                          smp.ctypes.data if ks >= 0 else None, None, 1)
+            assert rc == 0 and np.array_equal(jac2, jac) and np.array_equal(jacs2, jacs)
+        for i in range(B):
+            o = oracle.jacobian_ex(d, jv[i], mode, i_sample=ks, **kw)
+            assert n[i] == o["n"]
+            dp, ang = util.pose_errors(o["tip"][None], tip[i][None])
+            assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+            # finite differences divide the 1e-13-level arithmetic differences by the step
+            assert np.abs(o["jac"] - jac[i]).max() < 1e-6
+            if ks >= 0:
+                dp, ang = util.pose_errors(o["sample"][None], smp[i][None])
+                assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+                assert np.abs(o["jac_sample"] - jacs[i]).max() < 1e-6
