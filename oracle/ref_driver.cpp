@@ -274,3 +274,13 @@ int ctr_ref_jacobian_sample(void* h, const double* jv, int32_t nsamples, int32_t
 }
 
 }  // extern "C"
+
+// ---- the adapter a user of the reference includes (include/ctr_fk_reference_adapter.hpp), exercised on a live
+// reference robot (the header calls nothing of libctrfk.so).
+#include "../include/ctr_fk_reference_adapter.hpp"
+extern "C" int ctr_ref_adapter_desc(void* h, ctr_robot_desc* out)
+{
+    RefRobot* r = static_cast<RefRobot*>(h);
+    if (!r) return -1;
+    return ctr_fk_desc_from_reference(*r, out);
+}

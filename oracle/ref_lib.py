@@ -49,6 +49,7 @@ def load():
         lib.ctr_ref_degree_stability.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P]
         lib.ctr_ref_random_joints.argtypes = [_P, C.c_int64, _P]
         lib.ctr_ref_max_threads.restype = C.c_int
+        lib.ctr_ref_adapter_desc.argtypes = [_P, _P]
         lib.ctr_ref_jacobian_step.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P]
         lib.ctr_ref_jacobian_sample.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P]
         lib.ctr_ref_gamma_scale.argtypes = [C.c_int, C.c_double, _P, C.c_int64, _P]
@@ -147,6 +148,14 @@ class RefRobot:
         if rc != 0:
             raise RuntimeError("reference degree_stability error %d" % rc)
         return deg.value, st.value
+
+    def adapter_desc(self, desc_type):
+        """include/ctr_fk_reference_adapter.hpp applied to this live robot; returns a `desc_type` (ctrfk.RobotDesc)."""
+        d = desc_type()
+        rc = load().ctr_ref_adapter_desc(self.h, C.addressof(d))
+        if rc != 0:
+            raise RuntimeError("adapter error %d" % rc)
+        return d
 
     def random_joints(self, B):
         """B consecutive getRandomJointValues draws from a default std::mt19937 (ctr_test.cpp:30-32)."""

@@ -281,3 +281,27 @@ def test_jacobian_other_forms_bit_equal(ctrfk, oracle, robots, refs, name):
             assert np.array_equal(o["jac"], jt) and np.array_equal(o["jac_sample"], js)
         # the tip is the last sample
         assert np.array_equal(o["jac"], o["jac_sample"])
+
+
+def test_adapter_from_live_reference_robot(ctrfk, oracle, robots):
+    """include/ctr_fk_reference_adapter.hpp: the descriptor of a live CTR::Robot<double>, through its public
+    interface only (sections from getSection, entry frame observed through one FK call of the all-zero joint
+    vector).  Equals the descriptor of ctr_fk_desc_from_xml: sections exactly, entry frame to rounding of the
+    orthogonalisation; robots built from sections get their entry frame back bit for bit."""
+    for n in NAMES + ["sec3_tub4_v2.xml"]:
+        d = ctrfk.desc_from_xml(ctrfk.resource(n), 200)
+        a = ref_lib.RefRobot.from_xml(ctrfk.resource(n), 200).adapter_desc(ctrfk.RobotDesc)
+        assert (a.nsections, a.max_samples) == (d.nsections, 200)
+        assert bytes(a.sec) == bytes(d.sec)
+        assert np.abs(np.array(list(a.init_trafo)) - np.array(list(d.init_trafo))).max() < 1e-15
+        assert ctrfk.load().ctr_fk_desc_validate(a) == 0
+    rng = np.random.default_rng(5)
+    for layout in util.ALL_LAYOUTS:
+        d = util.random_robot(ctrfk, rng, layout)
+        a = ref_lib.RefRobot.from_desc(d).adapter_desc(ctrfk.RobotDesc)
+        assert list(a.init_trafo) == list(d.init_trafo)
+        for s in range(d.nsections):      # a CC section carries nothing in its [1] slots
+            k = d.sec[s].ntube
+            for f in ("stiffness", "curvature", "radius", "poisson"):
+                assert list(getattr(a.sec[s], f))[:k] == list(getattr(d.sec[s], f))[:k]
+            assert a.sec[s].ntube == k and a.sec[s].length == d.sec[s].length
