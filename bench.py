@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--soa", action="store_true", help="with --backbone: [MaxS][12][B] output layout (CTR_FK_FLAG_SOA)")
     ap.add_argument("--f32", action="store_true", help="FP32 state arithmetic variant")
     ap.add_argument("--shoot", action="store_true", help="base-angle shooting solve (ctr_fk_batch_base) instead of FK")
+    ap.add_argument("--shoot-max-iter", type=int, default=24,
+                    help="Newton iteration cap of --shoot (99.9 %% of the converging configurations need <= 18)")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer end-to-end leg (very large batches)")
@@ -286,7 +288,7 @@ def main():
     def one_step(i):
         s = i % NSET
         if a.shoot:
-            eng.batch_base(shoot[s]["jvb"], B, mode, step=step_len, nsamples=a.nsamples, tol=1e-11, max_iter=60,
+            eng.batch_base(shoot[s]["jvb"], B, mode, step=step_len, nsamples=a.nsamples, tol=1e-11, max_iter=a.shoot_max_iter,
                            jv_tip=shoot[s]["jt"], tip=tips[s], iters=shoot[s]["it"], status=shoot[s]["st"], stream=stream)
         elif a.f32:
             eng.batch_f32(jvs[s], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[s], stream=stream)

@@ -225,6 +225,9 @@ int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double a
  *   iters  [B]        out, nullable: Newton updates applied
  *   status [B]        out, nullable: 0 converged (max |base - wanted| <= tol), 1 Phi out of range,
  *                     2 singular Jacobian (bifurcation point), 3 max_iter reached
+ * max_iter: on the shipped robots 99 % of the converging configurations need <= 11 Newton updates and 99.9 %
+ * <= 18; 3.7 % of random inputs never converge (these robots are unstable there) and a lane holding one runs
+ * alone to the cap, which sets the tail of the persistent kernel — 24 is a good cap, 60 buys 0.08 % more roots.
  * DEVICE pointers. */
 #define CTR_FK_SHOOT_OK        0
 #define CTR_FK_SHOOT_PHI_RANGE 1

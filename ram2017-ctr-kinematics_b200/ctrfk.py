@@ -236,7 +236,7 @@ class Engine:
         _check(load().ctr_fk_stability_batch(self.handle, _ptr(jv), B, angle_step, arc_step, min_degree,
                                              _ptr(stable), _ptr(degree), stream))
 
-    def batch_base(self, jv_base, B, mode, step=0.0, nsamples=0, tol=1e-11, max_iter=60, jv_tip=None, tip=None,
+    def batch_base(self, jv_base, B, mode, step=0.0, nsamples=0, tol=1e-11, max_iter=24, jv_tip=None, tip=None,
                    iters=None, status=None, stream=None):
         _check(load().ctr_fk_batch_base(self.handle, _ptr(jv_base), B, mode, step, nsamples, tol, max_iter,
                                         _ptr(jv_tip), _ptr(tip), _ptr(iters), _ptr(status), stream))
