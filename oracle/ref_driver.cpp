@@ -284,3 +284,59 @@ extern "C" int ctr_ref_adapter_desc(void* h, ctr_robot_desc* out)
     if (!r) return -1;
     return ctr_fk_desc_from_reference(*r, out);
 }
+
+// ---- the float instantiation of the reference (CT_ROBOT_FLOAT, ctr_robot.cpp:724-731) -----------------------
+// Only to put the FP32 variant's error next to the reference's own single-precision build.  Note: real Eigen
+// 3.3.3 evaluates Array<float>::sin()/cos() with its SSE psin/pcos approximations; the stand-in uses libm's
+// sinf/cosf, which are at least as accurate — so this is a lower bound of the reference's float error.
+typedef CTR::Robot<float> RefRobotF;
+
+extern "C" {
+
+void* ctr_ref_create_desc_f32(const ctr_robot_desc* d)
+{
+    typedef CTR::types::SecCC<float> SecCC;
+    typedef CTR::types::SecVC<float> SecVC;
+    std::vector<std::pair<SecCC, size_t>> cc;
+    std::vector<std::pair<SecVC, size_t>> vc;
+    for (int s = 0; s < d->nsections; ++s) {
+        const ctr_section_desc& q = d->sec[s];
+        if (q.ntube == 1) {
+            SecCC c({float(q.stiffness[0])}, {float(q.curvature[0])}, float(q.length), {float(q.radius[0])}, {float(q.poisson[0])});
+            cc.push_back(std::make_pair(c, size_t(s)));
+        } else {
+            std::array<float, 2> k{{float(q.stiffness[0]), float(q.stiffness[1])}}, u{{float(q.curvature[0]), float(q.curvature[1])}},
+                r{{float(q.radius[0]), float(q.radius[1])}}, p{{float(q.poisson[0]), float(q.poisson[1])}};
+            SecVC v(k, u, float(q.length), r, p);
+            vc.push_back(std::make_pair(v, size_t(s)));
+        }
+    }
+    const double* t = d->init_trafo;
+    float f[12];
+    for (int i = 0; i < 12; ++i) f[i] = (float)t[i];
+    RefRobotF::Transform init(f[0], f[3], f[6], f[9], f[1], f[4], f[7], f[10], f[2], f[5], f[8], f[11]);
+    RefRobotF* r = new RefRobotF(size_t(d->max_samples), init, cc, vc);
+    if (!r->init()) { delete r; return nullptr; }
+    return r;
+}
+void ctr_ref_destroy_f32(void* h) { delete static_cast<RefRobotF*>(h); }
+
+// joint values in double (rounded to float on entry), tip out in double (widened), column-major 3x4
+int ctr_ref_fk_batch_f32(void* h, const double* jv, int64_t B, int mode, double step, int32_t nsamples, double* tip, int32_t* n_out)
+{
+    RefRobotF* r = static_cast<RefRobotF*>(h);
+    if (!r || !r->init()) return -1;
+    const int nj = int(r->getNJointValues());
+    RefRobotF::VectorJ q(nj, 1);
+    for (int64_t i = 0; i < B; ++i) {
+        for (int j = 0; j < nj; ++j) q[j] = float(jv[i * nj + j]);
+        float hret = 0.f, t12[12];
+        RefRobotF::Transform t = (mode == 0) ? r->calcKinematic(q, float(step), hret) : r->calcKinematic(q, size_t(nsamples), hret);
+        t.getData(t12, Erl::ColMajor);
+        for (int e = 0; e < 12; ++e) tip[12 * i + e] = double(t12[e]);
+        if (n_out) n_out[i] = int32_t(r->getNSamples());
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -49,6 +49,10 @@ def load():
         lib.ctr_ref_degree_stability.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P]
         lib.ctr_ref_random_joints.argtypes = [_P, C.c_int64, _P]
         lib.ctr_ref_max_threads.restype = C.c_int
+        lib.ctr_ref_create_desc_f32.restype = _P
+        lib.ctr_ref_create_desc_f32.argtypes = [_P]
+        lib.ctr_ref_destroy_f32.argtypes = [_P]
+        lib.ctr_ref_fk_batch_f32.argtypes = [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, _P, _P]
         lib.ctr_ref_adapter_desc.argtypes = [_P, _P]
         lib.ctr_ref_jacobian_step.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P]
         lib.ctr_ref_jacobian_sample.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P]
@@ -166,6 +170,22 @@ class RefRobot:
 
 def max_threads():
     return load().ctr_ref_max_threads()
+
+
+def fk_batch_f32(desc, jv, mode, step=0.0, nsamples=0):
+    """CTR::Robot<float> (the reference's single-precision instantiation, ctr_robot.cpp:724-731; sin/cos from libm's
+    sinf/cosf where real Eigen uses its SSE approximations).  Returns dict(tip [B][12] as double, n)."""
+    jv = np.ascontiguousarray(jv, dtype=np.float64)
+    h = load().ctr_ref_create_desc_f32(C.addressof(desc))
+    if not h:
+        raise RuntimeError("reference float robot construction failed")
+    B = jv.shape[0]
+    tip = np.zeros((B, 12)); n = np.zeros(B, np.int32)
+    rc = load().ctr_ref_fk_batch_f32(h, jv.ctypes.data, B, mode, step, nsamples, tip.ctypes.data, n.ctypes.data)
+    load().ctr_ref_destroy_f32(h)
+    if rc != 0:
+        raise RuntimeError("reference f32 error %d" % rc)
+    return dict(tip=tip, n=n)
 
 
 def gamma_scale(lut_size, gamma, u):

@@ -382,7 +382,15 @@ int ctr_fk_jacobian_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, int m
     a.mode = mode; a.step = step; a.i_sample = i_sample < 0 ? -1 : i_sample;
     a.jac_sample = i_sample >= 0 ? jac_sample : nullptr; a.sample = i_sample >= 0 ? sample : nullptr; a.n_out = n_out;
     a.given = given ? 1 : 0;
+    a.order = nullptr;
+    int32_t* order = nullptr;
+    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples) {
+        cudaError_t eo = make_order(h, jv, B, mode, step, nsamples, &order, (cudaStream_t)stream);
+        if (eo != cudaSuccess) return cuda_fail("step-mode binning", eo);
+        a.order = order;
+    }
     cudaError_t e = launch_jacobian(h->key, h->rb, a, (cudaStream_t)stream);
+    if (order) cudaFreeAsync(order, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail("jacobian kernel launch", e);
     return 0;
 }

@@ -12,8 +12,11 @@ __global__ void __launch_bounds__(kBlock)
 fk_jacobian_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ JacArgs a)
 {
     constexpr int NJ = L::NJ;
-    const int64_t cfg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (cfg >= a.B) return;
+    const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (slot >= a.B) return;
+    // ArcLengthStep form: sample counts differ per configuration; `order` lists every window of 4096
+    // configurations longest-sweep-first (bin_local_kernel), so a warp sees near-uniform counts
+    const int64_t cfg = a.order ? (int64_t)a.order[slot] : slot;
     double q[NJ];
     load_jv<L>(a.jv, cfg, q);
     jacobian_config<L, WITH_SAMPLE>(rb, q, a.mode, a.step, a.nsamples, a.i_sample, a.fd_trans, a.fd_rot,

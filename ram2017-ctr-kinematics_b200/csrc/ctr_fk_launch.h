@@ -43,6 +43,7 @@ struct JacArgs {
     double*       sample;       // [B][12] nullable
     int32_t*      n_out;        // [B] nullable
     int           given;        // tip / sample are inputs (CTR_FK_FLAG_JAC_GIVEN_POSES)
+    const int32_t* order;       // nullable: visiting order (step mode, window-local binning)
 };
 
 struct StabArgs {

@@ -220,10 +220,10 @@ class Engine:
                                            _ptr(jac), _ptr(tip)))
 
     def jacobian_ex(self, jv, B, mode, fd_trans, fd_rot, jac, step=0.0, nsamples=0, i_sample=-1, jac_sample=None,
-                    tip=None, sample=None, n_out=None, given=False, stream=None):
+                    tip=None, sample=None, n_out=None, given=False, flags=0, stream=None):
         """Every calcJacobian form (include/ctr_fk.h: ctr_fk_jacobian_batch_ex), device pointers."""
         _check(load().ctr_fk_jacobian_batch_ex(self.handle, _ptr(jv), B, mode, step, nsamples, i_sample, fd_trans, fd_rot,
-                                               FLAG_JAC_GIVEN_POSES if given else 0, _ptr(jac), _ptr(jac_sample), _ptr(tip),
+                                               flags | (FLAG_JAC_GIVEN_POSES if given else 0), _ptr(jac), _ptr(jac_sample), _ptr(tip),
                                                _ptr(sample), _ptr(n_out), stream))
 
     def jacobian_host_ex(self, jv, B, mode, fd_trans, fd_rot, jac, step=0.0, nsamples=0, i_sample=-1, jac_sample=None,

@@ -373,8 +373,15 @@ def test_jacobian_other_forms(ctrfk, oracle, robots, engines, name):
             eng.jacobian_host_ex(jv_np, B, 1, 1e-5, 1e-4, J2, nsamples=100, i_sample=ks, jac_sample=Js2, tip=T, sample=Sm, given=True)
             ok = np.arange(B) != 3
             assert np.array_equal(J2[ok], J[ok]) and np.array_equal(Js2[ok], Js[ok])
-    # the step form reproduces the reference's mixing of two discretisations: its columns differ from the NSamples
-    # form at the same sample count by O(h)/dq
+    # ArcLengthStep form on a batch large enough for the window-local binning: same bits with and without it
+    Bb = 20_000
+    jvb = torch.from_numpy(ctrfk.sample_joints_host(d, 24, 0, Bb)).cuda()
+    ja = torch.zeros(Bb, nj, 6, dtype=torch.float64, device="cuda"); jb = torch.zeros_like(ja)
+    na = torch.zeros(Bb, dtype=torch.int32, device="cuda"); nb = torch.zeros_like(na)
+    eng.jacobian_ex(jvb, Bb, 0, 1e-5, 1e-4, ja, step=d.max_length / 256.0, n_out=na, stream=st)
+    eng.jacobian_ex(jvb, Bb, 0, 1e-5, 1e-4, jb, step=d.max_length / 256.0, n_out=nb, flags=ctrfk.FLAG_NO_BINNING, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(ja, jb) and torch.equal(na, nb) and int(na.min()) < int(na.max())
     with pytest.raises(ctrfk.CtrFkError):
         eng.jacobian_ex(jv, B, 1, 1e-5, 1e-4, jac, nsamples=100, i_sample=5, stream=st)       # no jac_sample buffer
 

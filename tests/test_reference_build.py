@@ -305,3 +305,22 @@ def test_adapter_from_live_reference_robot(ctrfk, oracle, robots):
             for f in ("stiffness", "curvature", "radius", "poisson"):
                 assert list(getattr(a.sec[s], f))[:k] == list(getattr(d.sec[s], f))[:k]
             assert a.sec[s].ntube == k and a.sec[s].length == d.sec[s].length
+
+
+def test_f32_variant_next_to_the_reference_float_build(ctrfk, oracle, hostsim, robots):
+    """The FP32 variant (per-thread solvers compiled for the CPU) and the reference's own float instantiation
+    (CTR::Robot<float>, with libm sinf/cosf standing in for Eigen's SSE approximations), both against the FP64
+    oracle: the variant stays inside its stated tolerance (1e-4 m / 1e-3 rad) and is closer to the FP64 result
+    than the reference's float build — whose control scalars (arc positions, interval compares, Erl::equal's
+    float tolerance) are single precision too, so single samples change section."""
+    for name in util.ROBOT_FILES:
+        d = robots[name]
+        jv = ctrfk.sample_joints_host(d, util.SEEDS[name], 0, 4000)
+        o = oracle.fk_batch(d, jv, ctrfk.MODE_NSAMPLE, nsamples=256)
+        r = ref_lib.fk_batch_f32(d, jv, ctrfk.MODE_NSAMPLE, nsamples=256)
+        dpr, angr = util.pose_errors(o["tip"], r["tip"])
+        for fast in (2, 3):
+            s = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=256, fast=fast)
+            dp, ang = util.pose_errors(o["tip"], s["tip"])
+            assert dp.max() <= 1e-4 and ang.max() <= 1e-3
+            assert dp.mean() < dpr.mean() and dp.max() < dpr.max()
