@@ -424,7 +424,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * e2e_steps / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": B * njv * 8, "d2h_bytes_per_step": B * 12 * 8, "steps": e2e_steps,
-               "api": "ctr_fk_batch_host (host pointers in, tip poses out; chunked H2D/solve/D2H on 3 streams)",
+               "api": "ctr_fk_batch_host (host pointers in, tip poses out; chunked H2D/solve/D2H on 4 streams)",
                "pcie_measured": pcie,
                "bound": "PCIe: %.0f MB out per step at the measured D2H rate caps this at %.3g configurations/s" % (
                    B * 96 / 1e6, B / (B * 96 / 1e9 / pcie["d2h_GBs"]))}

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -24,7 +25,9 @@ struct ctr_fk_engine {
     int            njv;
     int            ntubes;
     int            sm_count;
-    static constexpr int kStreams = 3;
+    static constexpr int kStreams = 8;      // created; ctr_fk_batch_host uses host_streams of them
+    int            host_streams; // pipeline depth of the host-pointer path (4; CTRFK_HOST_STREAMS overrides, for tuning)
+    int            host_chunk_waves; // chunk size of the host-pointer path in waves of the tip kernel (1; CTRFK_HOST_CHUNK_WAVES)
     cudaStream_t   streams[kStreams];
     std::mutex     host_mu;      // serialises ctr_fk_batch_host / ctr_fk_single calls on one handle
     char*          single_buf;   // device scratch of ctr_fk_single (lazily allocated)
@@ -174,6 +177,10 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
     h->njv = 1 + desc->nsections + h->ntubes;
     h->sm_count = prop.multiProcessorCount;
     for (int i = 0; i < ctr_fk_engine::kStreams; ++i) h->streams[i] = nullptr;
+    h->host_streams = 4;
+    h->host_chunk_waves = 1;
+    if (const char* ev = std::getenv("CTRFK_HOST_STREAMS")) { const int v = std::atoi(ev); if (v >= 1 && v <= ctr_fk_engine::kStreams) h->host_streams = v; }
+    if (const char* ev = std::getenv("CTRFK_HOST_CHUNK_WAVES")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) h->host_chunk_waves = v; }
     h->single_buf = nullptr;
     h->stage_buf = nullptr;
     h->stage_bytes = 0;
@@ -232,10 +239,10 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     std::lock_guard<std::mutex> lock(h->host_mu);
 
-    constexpr int NS = ctr_fk_engine::kStreams;
+    const int NS = h->host_streams;
     // one chunk = one full wave of the tip kernel (4 CTAs of kBlock threads per SM): a chunk that
     // fills only part of the resident slots would pay a whole wave time for less work
-    const int64_t wave = (int64_t)h->sm_count * 4 * kBlock;
+    const int64_t wave = (int64_t)h->sm_count * 4 * kBlock * h->host_chunk_waves;
     const int64_t chunk = std::min<int64_t>(wave > 0 ? wave : kHostChunk, B);
     const int njv = h->njv;
     // one slab per stream: jv | tip | n_out | step_out | status
