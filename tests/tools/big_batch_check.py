@@ -2,7 +2,7 @@
 """BASELINE config 5 in one launch on one GPU: 100M configurations of ctr_sec3_tub5 generated on
 the device, solved by one ctr_fk_batch call (FP64) and one ctr_fk_batch_f32 call, slices checked
 against the CPU oracle (64-bit indexing, grid sizes beyond 2^16 CTAs).
-   python tools/big_batch_check.py [B]"""
+   python tests/tools/big_batch_check.py [B]"""
 import os
 import sys
 import time
@@ -12,7 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p in ("ram2017-ctr-kinematics_b200", "oracle", "tests"):
-    sys.path.insert(0, os.path.join(HERE, "..", p))
+    sys.path.insert(0, os.path.join(HERE, "..", "..", p))
 import ctrfk  # noqa: E402
 import oracle_lib  # noqa: E402
 import util  # noqa: E402

@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in ("ram2017-ctr-kinematics_b200", "oracle", "tests"):
     sys.path.insert(0, os.path.join(REPO, p))
 import ctrfk      # noqa: E402
