@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--shoot-max-iter", type=int, default=24,
                     help="Newton iteration cap of --shoot (99.9 %% of the converging configurations need <= 18)")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
+    ap.add_argument("--allgather-fused", choices=["ipc", "symm", "multicast"], default=None,
+                    help="solve + all-gather in ONE kernel (ctr_fk_batch_gather): poses stored straight into every rank's "
+                         "gathered buffer over NVLink; ipc = buffers shared by CUDA IPC (ctr_fk_peer_*), symm = torch "
+                         "symmetric memory, multicast = its NVSwitch multicast address (one multimem.st per 16 bytes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer end-to-end leg (very large batches)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="configurations of the CPU baseline sample (0 = auto)")
@@ -270,6 +274,46 @@ def main():
             rds.append(torch.empty(B, a.max_samples, dtype=torch.float64, device="cuda"))
     gathered = torch.empty(world * B, 12, dtype=torch.float64, device="cuda") if (a.allgather and world > 1) else None
 
+    # ---- fused solve + all-gather: every rank's gathered buffer mapped into every process ------------------
+    fused = None
+    if a.allgather_fused and world > 1:
+        if a.f32 or a.backbone or a.shoot or a.strict:
+            raise SystemExit("--allgather-fused applies to the FP64 tip solve")
+        nbytes = world * B * 96
+
+        class _Raw:      # zero-copy torch view of a raw device pointer
+            def __init__(self, ptr, rows):
+                self.__cuda_array_interface__ = {"shape": (rows, 12), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+        if a.allgather_fused == "ipc":
+            mine, handle = eng.peer_alloc(nbytes)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            ptrs = [mine if r == rank else eng.peer_open(handles[r]) for r in range(world)]
+            fused = dict(ptrs=ptrs, mc=False, view=torch.as_tensor(_Raw(mine, world * B), device="cuda"), keep=(mine, handles))
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty((world * B, 12), dtype=torch.float64, device=torch.device("cuda", local))
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if a.allgather_fused == "multicast":
+                if not hdl.has_multicast_support or not hdl.multicast_ptr:
+                    raise SystemExit("no NVSwitch multicast support reported by torch symmetric memory")
+                fused = dict(ptrs=[int(hdl.multicast_ptr)], mc=True, view=buf, keep=(buf, hdl))
+            else:
+                fused = dict(ptrs=[int(p) for p in hdl.buffer_ptrs], mc=False, view=buf, keep=(buf, hdl))
+        fused["flag"] = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # check once against NCCL: one fused step, a rank barrier, then the same poses gathered by all_gather_into_tensor
+        eng.batch_gather(jvs[0], B, mode, fused["ptrs"], rank * B, step=step_len, nsamples=a.nsamples, flags=flags,
+                         multicast=fused["mc"], stream=stream)
+        dist.all_reduce(fused["flag"])
+        eng.batch(jvs[0], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[0], stream=stream)
+        want = torch.empty(world * B, 12, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(want, tips[0])
+        torch.cuda.synchronize()
+        if not torch.equal(fused["view"], want):
+            raise SystemExit("fused all-gather differs from NCCL all_gather_into_tensor")
+        del want
+
     shoot = None
     if a.shoot:
         # inputs: base angles reached from the random tip angles (so a root exists for every input)
@@ -292,6 +336,12 @@ def main():
                            jv_tip=shoot[s]["jt"], tip=tips[s], iters=shoot[s]["it"], status=shoot[s]["st"], stream=stream)
         elif a.f32:
             eng.batch_f32(jvs[s], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[s], stream=stream)
+        elif fused is not None:
+            # one kernel solves and stores every pose into all ranks' gathered buffers; the one-element all-reduce
+            # is the rank barrier after which every rank's buffer is complete (what an all-gather guarantees)
+            eng.batch_gather(jvs[s], B, mode, fused["ptrs"], rank * B, step=step_len, nsamples=a.nsamples, flags=flags,
+                             multicast=fused["mc"], stream=stream)
+            dist.all_reduce(fused["flag"])
         else:
             eng.batch(jvs[s], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[s],
                       backbone=bbs[s] if a.backbone else None, radius=rds[s] if a.backbone else None, stream=stream)
@@ -449,7 +499,9 @@ def main():
                 "config": {"workload": workload_name(a), "robot": a.robot, "mode": a.mode, "nsamples": a.nsamples,
                            "batch_per_gpu": B, "arithmetic": "strict" if a.strict else "fast",
                            "l2": "two alternating input/output sets of %.0f MB each (> 126 MB L2 together and singly)" % ((njv * 8 + 96) * B / 1e6),
-                           "collective": "all_gather(tip)" if gathered is not None else "none"},
+                           "collective": ("all_gather(tip)" if gathered is not None else
+                                          ("fused into the solver kernel: NVLink peer stores (%s) + 1-element all-reduce as rank barrier, "
+                                           "checked equal to all_gather_into_tensor" % a.allgather_fused) if fused is not None else "none")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches}
         if a.shoot:
             it = shoot[0]["it"].cpu().numpy(); stt = shoot[0]["st"].cpu().numpy()

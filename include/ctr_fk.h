@@ -41,6 +41,7 @@
 #ifndef CTR_FK_H
 #define CTR_FK_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -154,6 +155,31 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
 int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                       int32_t nsamples, uint32_t flags,
                       double* tip, int32_t* n_out, double* step_out, int32_t* status);
+
+/* Solve + all-gather in ONE kernel (the optional all-gather of the poses over NVLink).  Every rank
+ * calls this on its own slice; each thread stores its pose into row `first_row + i` of EVERY destination buffer —
+ * the gathered [world * B][12] buffers of all ranks, mapped into this process (CUDA IPC: ctr_fk_peer_alloc /
+ * ctr_fk_peer_open below, or torch symmetric memory), so the transfer is NVLink peer stores issued by the solver
+ * warps while the others keep the FP64 pipe busy; no separate collective, no staging copy.
+ *   tip_dst   HOST array of `ndst` (1..8) DEVICE pointers, one per destination rank (this rank's own buffer included)
+ *   flags     CTR_FK_FLAG_GATHER_MULTICAST: tip_dst[0] is an NVSwitch multicast address (ndst = 1); one
+ *             multimem.st per 16 bytes, replicated to every GPU by the switch.  CTR_FK_FLAG_NO_BINNING as usual.
+ *   first_row this rank's first row in the gathered buffer (ctr_fk shards contiguously: rank * B)
+ * Stores to peers are complete when the kernel is; the caller synchronises the RANKS before reading the gathered
+ * buffer (a barrier).  FAST arithmetic, tip poses only.  n_out/step_out/status: local [B], nullable. */
+#define CTR_FK_FLAG_GATHER_MULTICAST 0x200u
+int ctr_fk_batch_gather(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                        int32_t nsamples, uint32_t flags, void* const* tip_dst, int32_t ndst,
+                        int64_t first_row, int32_t* n_out, double* step_out, int32_t* status,
+                        void* stream);
+/* Peer-visible device buffers for it, one process per GPU: ctr_fk_peer_alloc allocates `bytes` on the engine's
+ * device and returns a 64-byte CUDA IPC handle to hand to the other ranks (any byte transport);
+ * ctr_fk_peer_open maps a peer's buffer into this process (peer access is enabled on first use);
+ * ctr_fk_peer_close / ctr_fk_peer_free undo them. */
+int ctr_fk_peer_alloc(ctr_fk_handle h, size_t bytes, void** dptr, unsigned char* handle64);
+int ctr_fk_peer_open(ctr_fk_handle h, const unsigned char* handle64, void** dptr);
+int ctr_fk_peer_close(ctr_fk_handle h, void* dptr);
+int ctr_fk_peer_free(ctr_fk_handle h, void* dptr);
 
 /* One configuration, HOST pointers, synchronous: the reference's single-shot call
  * (robot_i.h:690-755) served by the same kernels with B = 1.  The handle keeps a small device

@@ -229,6 +229,93 @@ int ctr_fk_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double 
                      alpha_base, status, (cudaStream_t)stream);
 }
 
+int ctr_fk_batch_gather(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                        uint32_t flags, void* const* tip_dst, int32_t ndst, int64_t first_row, int32_t* n_out,
+                        double* step_out, int32_t* status, void* stream)
+{
+    int rc = check_common(h, jv, B, mode, step, nsamples);
+    if (rc) return rc;
+    if (flags & CTR_FK_FLAG_STRICT) { set_error("ctr_fk_batch_gather: FAST arithmetic only"); return CTR_FK_E_ARG; }
+    const bool mc = (flags & CTR_FK_FLAG_GATHER_MULTICAST) != 0;
+    if (!tip_dst || ndst < 1 || ndst > 8 || (mc && ndst != 1) || first_row < 0) {
+        set_error("ctr_fk_batch_gather: 1..8 destination buffers (exactly 1 multicast address), first_row >= 0");
+        return CTR_FK_E_ARG;
+    }
+    for (int p = 0; p < ndst; ++p)
+        if (!tip_dst[p] || !aligned16(tip_dst[p])) { set_error("ctr_fk_batch_gather: destination %d null or not 16-byte aligned", p); return CTR_FK_E_ARG; }
+    if ((rc = check_align(h, jv, nullptr, nullptr))) return rc;
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    cudaStream_t st = (cudaStream_t)stream;
+    FkArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.jv = jv; a.B = B; a.mode = mode; a.step = step; a.nsamples = nsamples;
+    a.n_out = n_out; a.step_out = step_out; a.status = status;
+    for (int p = 0; p < ndst; ++p) a.gather[p] = (double*)tip_dst[p];
+    a.ngather = ndst; a.gather_mc = mc ? 1 : 0; a.gather_row = first_row;
+    int32_t* order = nullptr;
+    if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples) {
+        cudaError_t eo = make_order(h, jv, B, mode, step, nsamples, &order, st);
+        if (eo != cudaSuccess) return cuda_fail("step-mode binning", eo);
+        a.order = order;
+    }
+    cudaError_t e = launch_tip_gather(h->key, h->rb, a, st);
+    if (order) cudaFreeAsync(order, st);
+    if (e != cudaSuccess) return cuda_fail("solver kernel launch", e);
+    return 0;
+}
+
+// ---- peer-visible buffers for ctr_fk_batch_gather (CUDA IPC; one process per GPU) -------------------------
+int ctr_fk_peer_alloc(ctr_fk_handle h, size_t bytes, void** dptr, unsigned char* handle64)
+{
+    if (!h || !dptr || !handle64) { set_error("ctr_fk_peer_alloc: null argument"); return CTR_FK_E_NULL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_peer_alloc: cudaMalloc", e);
+    cudaIpcMemHandle_t hd;
+    e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail("ctr_fk_peer_alloc: cudaIpcGetMemHandle", e); }
+    std::memcpy(handle64, &hd, 64);
+    *dptr = p;
+    return 0;
+}
+
+int ctr_fk_peer_open(ctr_fk_handle h, const unsigned char* handle64, void** dptr)
+{
+    if (!h || !dptr || !handle64) { set_error("ctr_fk_peer_open: null argument"); return CTR_FK_E_NULL; }
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_peer_open: cudaIpcOpenMemHandle", e);
+    return 0;
+}
+
+int ctr_fk_peer_close(ctr_fk_handle h, void* dptr)
+{
+    if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
+    if (!dptr) return 0;
+    DeviceGuard g(h->device);
+    cudaError_t e = cudaIpcCloseMemHandle(dptr);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_peer_close", e);
+    return 0;
+}
+
+int ctr_fk_peer_free(ctr_fk_handle h, void* dptr)
+{
+    if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
+    if (!dptr) return 0;
+    DeviceGuard g(h->device);
+    cudaError_t e = cudaFree(dptr);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_peer_free", e);
+    return 0;
+}
+
 int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
                       uint32_t flags, double* tip, int32_t* n_out, double* step_out, int32_t* status)
 {

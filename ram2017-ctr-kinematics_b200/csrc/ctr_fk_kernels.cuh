@@ -42,6 +42,31 @@ __device__ __forceinline__ void store_tf(double* dst, const double* t)
     for (int j = 0; j < 6; ++j) d2[j] = make_double2(t[2 * j], t[2 * j + 1]);
 }
 
+// the same row through an NVSwitch multicast mapping: one store, replicated to every GPU of the group by the
+// switch (multimem.st; SASS: STG.E.128.STRONG.SYS on the multicast address)
+__device__ __forceinline__ void store_tf_multicast(double* dst, const double* t)
+{
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const unsigned long long a = (unsigned long long)__double_as_longlong(t[2 * j]);
+        const unsigned long long b = (unsigned long long)__double_as_longlong(t[2 * j + 1]);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2 * j),
+                     "f"(__uint_as_float((unsigned)a)), "f"(__uint_as_float((unsigned)(a >> 32))),
+                     "f"(__uint_as_float((unsigned)b)), "f"(__uint_as_float((unsigned)(b >> 32)))
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void store_tf_gather(const FkArgs& a, int64_t cfg, const double* t)
+{
+    const int64_t row = (a.gather_row + cfg) * 12;
+    if (a.gather_mc) {
+        store_tf_multicast(a.gather[0] + row, t);
+        return;
+    }
+#pragma unroll 1
+    for (int p = 0; p < a.ngather; ++p) store_tf(a.gather[p] + row, t);
+}
+
 template <class L>
 __device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg)
 {
@@ -63,7 +88,9 @@ __device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg)
 // Register budget: 4 CTAs of 128 threads per SM (16 warps) leaves 128 registers per thread.  Measured
 // on B200 (tools/tune_tip.cu): capping registers for 20 or 24 warps/SM is 3-5 % slower — the sweep
 // is bound by FP64 issue, not by latency that more warps could hide.
-template <class L, bool FAST>
+// GATHER: the pose is stored into the gathered buffer of every rank (store_tf_gather) instead of `tip` —
+// solve and all-gather in one kernel; the stores ride NVLink while the other warps keep the FP64 pipe busy.
+template <class L, bool FAST, bool GATHER = false>
 __global__ void __launch_bounds__(kBlock, FAST ? 4 : 1)
 fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
@@ -84,14 +111,24 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
     load_jv<L>(a.jv, cfg, q);
     Ctl<L> c;
     setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-    if (c.status) { write_invalid<L>(a, cfg); return; }
+    if (c.status) {
+        write_invalid<L>(a, cfg);
+        if (GATHER) {
+            double nan12[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) nan12[j] = __longlong_as_double(0x7ff8000000000000ll);
+            store_tf_gather(a, cfg, nan12);
+        }
+        return;
+    }
 
     double tip[12];
     double alb[L::T];
     if (FAST) solve_fast<L, true>(rb, c, tip, a.alpha_base ? alb : nullptr, NoSample{});
-    else      solve_strict<L, true>(rb, c, a.tip ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
+    else      solve_strict<L, true>(rb, c, (a.tip || GATHER) ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
 
-    if (a.tip) store_tf(a.tip + cfg * 12, tip);
+    if (GATHER) store_tf_gather(a, cfg, tip);
+    else if (a.tip) store_tf(a.tip + cfg * 12, tip);
     if (a.radius) {
         if (a.soa) fill_radius<L>(rb, c, a.radius + cfg, a.B);
         else       fill_radius<L>(rb, c, a.radius + cfg * (int64_t)rb.maxs, 1);

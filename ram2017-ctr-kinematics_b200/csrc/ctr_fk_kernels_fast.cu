@@ -26,6 +26,28 @@ cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& args, cudaS
     return cudaGetLastError();
 }
 
+cudaError_t launch_tip_gather(int key, const KRobot& rb, const FkArgs& args, cudaStream_t st)
+{
+    if (args.B <= 0) return cudaSuccess;
+    FkArgs a = args;
+    unsigned grid = grid_for(a.B);
+    if (a.order) {
+        a.windows = (int)((a.B + kBinWindow - 1) / kBinWindow);
+        grid = (unsigned)a.windows * (kBinWindow / kBlock);
+    }
+    switch (key) {
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: \
+        fk_tip_kernel<Lay<S, A, Bq, C>, true, true><<<grid, kBlock, 0, st>>>(rb, a); \
+        break;
+        CTRK_FOR_EACH_LAYOUT_K(X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;

@@ -27,6 +27,12 @@ struct FkArgs {
     int            soa;         // backbone/radius layout
     int            windows;     // tip kernels, with `order`: number of binning windows; CTAs then walk the
                                 // windows rank-major (every window's longest sweeps first), 0 = linear
+    // solve + all-gather in one kernel (ctr_fk_batch_gather): every pose goes to row gather_row + cfg of each
+    // destination — peer-mapped gathered buffers (NVLink P2P stores) or one NVSwitch multicast mapping
+    double*        gather[8];
+    int            ngather;     // 0: plain `tip` output
+    int            gather_mc;   // destinations are multicast addresses: multimem.st
+    int64_t        gather_row;
 };
 
 struct JacArgs {
@@ -75,6 +81,7 @@ constexpr int kBinWindow = 4096;        // step-mode binning sorts windows of th
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
 cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+cudaError_t launch_tip_gather(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 cudaError_t launch_tip_strict(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 cudaError_t launch_tip_f32(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 // backbone solvers (two passes inside one kernel; the output buffer doubles as scratch)

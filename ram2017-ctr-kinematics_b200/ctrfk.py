@@ -15,6 +15,7 @@ MAX_SECTIONS = 3
 MAX_TUBES = 6
 MODE_STEP, MODE_NSAMPLE = 0, 1
 FLAG_JAC_GIVEN_POSES = 0x100
+FLAG_GATHER_MULTICAST = 0x200
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
@@ -69,6 +70,12 @@ SYMBOLS = {
                                     _P, _P, _P, _P]),
     "ctr_fk_single": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int32, C.c_uint32,
                                 _P, _P, _P, _P, _P, _P]),
+    "ctr_fk_batch_gather": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_uint32, _P, C.c_int32, C.c_int64,
+                                      _P, _P, _P, _P]),
+    "ctr_fk_peer_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P), _P]),
+    "ctr_fk_peer_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "ctr_fk_peer_close": (C.c_int, [_P, _P]),
+    "ctr_fk_peer_free": (C.c_int, [_P, _P]),
     "ctr_fk_jacobian_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P, _P]),
     "ctr_fk_jacobian_host": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P, _P]),
     "ctr_fk_jacobian_batch_ex": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double,
@@ -210,6 +217,34 @@ class Engine:
         if rc not in (0, STATUS_PHI_RANGE):
             _check(rc)
         return rc
+
+    def batch_gather(self, jv, B, mode, dst_ptrs, first_row, step=0.0, nsamples=0, flags=0, multicast=False, n_out=None,
+                     step_out=None, status=None, stream=None):
+        """Solve + all-gather in one kernel: dst_ptrs = device addresses (ints) of every rank's gathered buffer as
+        mapped in this process, or [multicast address] with multicast=True."""
+        arr = (_P * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+        _check(load().ctr_fk_batch_gather(self.handle, _ptr(jv), B, mode, step, nsamples,
+                                          flags | (FLAG_GATHER_MULTICAST if multicast else 0), arr, len(dst_ptrs), first_row,
+                                          _ptr(n_out), _ptr(step_out), _ptr(status), stream))
+
+    def peer_alloc(self, nbytes):
+        """(device pointer, 64-byte IPC handle) of a buffer other ranks can map with peer_open."""
+        p = _P()
+        hd = (C.c_ubyte * 64)()
+        _check(load().ctr_fk_peer_alloc(self.handle, nbytes, C.byref(p), C.cast(hd, _P)))
+        return p.value, bytes(hd)
+
+    def peer_open(self, handle64):
+        p = _P()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle64)
+        _check(load().ctr_fk_peer_open(self.handle, C.cast(buf, _P), C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr):
+        _check(load().ctr_fk_peer_close(self.handle, ptr))
+
+    def peer_free(self, ptr):
+        _check(load().ctr_fk_peer_free(self.handle, ptr))
 
     def jacobian(self, jv, B, nsamples, fd_trans, fd_rot, jac, tip=None, stream=None):
         _check(load().ctr_fk_jacobian_batch(self.handle, _ptr(jv), B, nsamples, fd_trans, fd_rot,

@@ -386,6 +386,36 @@ def test_jacobian_other_forms(ctrfk, oracle, robots, engines, name):
         eng.jacobian_ex(jv, B, 1, 1e-5, 1e-4, jac, nsamples=100, i_sample=5, stream=st)       # no jac_sample buffer
 
 
+def test_fused_gather_kernel_single_device(ctrfk, robots, engines):
+    """ctr_fk_batch_gather with the "ranks" emulated on one GPU (two local buffers stand in for two ranks' gathered
+    buffers; the multi-process path over NVLink is exercised by bench.py --allgather-fused): every destination gets
+    this rank's rows at first_row, bit-equal to ctr_fk_batch, invalid configurations as NaN rows, nothing else touched."""
+    name = "ctr_sec3_tub3.xml"
+    d, eng = robots[name], engines[name]
+    st = torch.cuda.current_stream().cuda_stream
+    for mode, kw, B in ((1, dict(nsamples=200), 3000), (0, dict(step=d.max_length / 256.0), 20_000)):
+        jv_np = ctrfk.sample_joints_host(d, 61, 0, B)
+        jv_np[7, 1] = -1.0
+        jv = torch.from_numpy(jv_np).cuda()
+        tip = torch.empty(B, 12, dtype=torch.float64, device="cuda")
+        n = torch.empty(B, dtype=torch.int32, device="cuda"); n2 = torch.empty_like(n)
+        eng.batch(jv, B, mode, tip=tip, n_out=n, stream=st, **kw)
+        first, rows = 5, B + 11
+        bufs = [torch.full((rows, 12), -3.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+        before = ctrfk.launch_count()
+        eng.batch_gather(jv, B, mode, [b.data_ptr() for b in bufs], first, n_out=n2, stream=st, **kw)
+        torch.cuda.synchronize()
+        assert ctrfk.launch_count() > before and torch.equal(n, n2)
+        for b in bufs:
+            assert torch.equal(b[first:first + B], tip) or (torch.isnan(tip[7]).all() and torch.isnan(b[first + 7]).all()
+                                                            and torch.equal(torch.nan_to_num(b[first:first + B]), torch.nan_to_num(tip)))
+            assert bool((b[:first] == -3.0).all()) and bool((b[first + B:] == -3.0).all())
+    with pytest.raises(ctrfk.CtrFkError):
+        eng.batch_gather(jv, B, 1, [], 0, nsamples=10, stream=st)
+    with pytest.raises(ctrfk.CtrFkError):
+        eng.batch_gather(jv, B, 1, [bufs[0].data_ptr()] * 2, 0, nsamples=10, multicast=True, stream=st)
+
+
 # ---- full-size, size-independent properties (BASELINE.json config 2: 1M configurations) --------
 
 def rz_batch(theta):
