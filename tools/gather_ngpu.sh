@@ -1,5 +1,5 @@
 #!/bin/bash
-# Fused solve + all-gather against NCCL, N GPUs of one box:  gpurun --gpus N -- bash tools/gather_2gpu.sh N
+# Fused solve + all-gather against NCCL, N GPUs of one box:  gpurun --gpus N -- bash tools/gather_ngpu.sh N
 N=${1:-2}
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 1000)) bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline --no-e2e "$@" 2>gpurun_out/gather_err.log | tail -1 | python -c "
 import sys, json
