@@ -79,3 +79,23 @@ def test_shard_ranges_tile_the_batch(ctrfk):
             for a, b in zip(spans, spans[1:]):
                 assert a[1] == b[0]
             assert max(hi - lo for lo, hi in spans) == -(-total // world)
+
+
+def test_reference_arm_under_torchrun_prints_once(tmp_path):
+    """`bench.py --impl reference` launched like the driver launches it for N > 1 (torchrun, one rank per GPU): rank 0
+    alone times the CPU arm and prints ONE JSON line, the other ranks exit 0 without work.  No GPU involved."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(repo, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--cpu-sample", "2000"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=repo)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
