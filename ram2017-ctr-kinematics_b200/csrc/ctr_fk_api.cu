@@ -517,10 +517,12 @@ int ctr_fk_jacobian_host_ex(ctr_fk_handle h, const double* jv, int64_t B, int mo
     const bool   ws = i_sample >= 0;
     const size_t b_jv = up256(sizeof(double) * njv * (size_t)B), b_jac = up256(sizeof(double) * 6 * njv * (size_t)B),
                  b_tip = up256(sizeof(double) * 12 * (size_t)B), b_n = up256(sizeof(int32_t) * (size_t)B);
+    // stream-ordered allocation from the device pool (kept cached, see ctr_fk_create): no device-wide
+    // synchronisation per call, which matters for the one-configuration calls of ctrb200::Robot
     char* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, b_jv + 2 * b_jac + 2 * b_tip + b_n);
-    if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: allocation", e);
     cudaStream_t st = h->streams[0];
+    cudaError_t e = cudaMallocAsync((void**)&d, b_jv + 2 * b_jac + 2 * b_tip + b_n, st);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: allocation", e);
     double*  d_jv   = (double*)d;
     double*  d_jac  = (double*)(d + b_jv);
     double*  d_jacs = (double*)(d + b_jv + b_jac);
@@ -541,8 +543,8 @@ int ctr_fk_jacobian_host_ex(ctr_fk_handle h, const double* jv, int64_t B, int mo
             if (e == cudaSuccess && n_out) e = cudaMemcpyAsync(n_out, d_n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st);
         }
     }
+    cudaFreeAsync(d, st);
     cudaError_t es = cudaStreamSynchronize(st);
-    cudaFree(d);
     if (rc) return rc;
     if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: copy", e);
     if (es != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: sync", es);
@@ -596,9 +598,9 @@ int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double a
     const size_t n_jv = sizeof(double) * (size_t)h->njv * (size_t)B;
     const size_t b_jv = up256(n_jv), b_deg = up256(sizeof(double) * (size_t)B), b_st = sizeof(int32_t) * (size_t)B;
     char* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, b_jv + b_deg + b_st);
-    if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: allocation", e);
     cudaStream_t st = h->streams[0];
+    cudaError_t e = cudaMallocAsync((void**)&d, b_jv + b_deg + b_st, st);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: allocation", e);
     double* d_jv = (double*)d;
     double* d_deg = (double*)(d + b_jv);
     int32_t* d_st = (int32_t*)(d + b_jv + b_deg);
@@ -610,8 +612,8 @@ int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double a
             if (e == cudaSuccess && degree) e = cudaMemcpyAsync(degree, d_deg, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st);
         }
     }
+    cudaFreeAsync(d, st);
     cudaError_t es = cudaStreamSynchronize(st);
-    cudaFree(d);
     if (rc) return rc;
     if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: copy", e);
     if (es != cudaSuccess) return cuda_fail("ctr_fk_stability_host: sync", es);
