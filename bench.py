@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--shoot-max-iter", type=int, default=24,
                     help="Newton iteration cap of --shoot (99.9 %% of the converging configurations need <= 18)")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
+    ap.add_argument("--gather-rowwise", action="store_true", help="--allgather-fused with one thread storing its own row (comparison)")
+    ap.add_argument("--gather-replicate", type=int, default=1,
+                    help="--allgather-fused ipc/symm: list every destination K times (emulates K times as many peers on a small box)")
     ap.add_argument("--allgather-fused", choices=["ipc", "symm", "multicast"], default=None,
                     help="solve + all-gather in ONE kernel (ctr_fk_batch_gather): poses stored straight into every rank's "
                          "gathered buffer over NVLink; ipc = buffers shared by CUDA IPC (ctr_fk_peer_*), symm = torch "
@@ -301,9 +304,12 @@ def main():
                 fused = dict(ptrs=[int(hdl.multicast_ptr)], mc=True, view=buf, keep=(buf, hdl))
             else:
                 fused = dict(ptrs=[int(p) for p in hdl.buffer_ptrs], mc=False, view=buf, keep=(buf, hdl))
+        if not fused["mc"] and a.gather_replicate > 1:
+            fused["ptrs"] = (fused["ptrs"] * a.gather_replicate)[:8]
+        fused["flags"] = flags | (ctrfk.FLAG_GATHER_ROWWISE if a.gather_rowwise else 0)
         fused["flag"] = torch.zeros(1, dtype=torch.int32, device="cuda")
         # check once against NCCL: one fused step, a rank barrier, then the same poses gathered by all_gather_into_tensor
-        eng.batch_gather(jvs[0], B, mode, fused["ptrs"], rank * B, step=step_len, nsamples=a.nsamples, flags=flags,
+        eng.batch_gather(jvs[0], B, mode, fused["ptrs"], rank * B, step=step_len, nsamples=a.nsamples, flags=fused["flags"],
                          multicast=fused["mc"], stream=stream)
         dist.all_reduce(fused["flag"])
         eng.batch(jvs[0], B, mode, step=step_len, nsamples=a.nsamples, flags=flags, tip=tips[0], stream=stream)
@@ -339,7 +345,7 @@ def main():
         elif fused is not None:
             # one kernel solves and stores every pose into all ranks' gathered buffers; the one-element all-reduce
             # is the rank barrier after which every rank's buffer is complete (what an all-gather guarantees)
-            eng.batch_gather(jvs[s], B, mode, fused["ptrs"], rank * B, step=step_len, nsamples=a.nsamples, flags=flags,
+            eng.batch_gather(jvs[s], B, mode, fused["ptrs"], rank * B, step=step_len, nsamples=a.nsamples, flags=fused["flags"],
                              multicast=fused["mc"], stream=stream)
             dist.all_reduce(fused["flag"])
         else:
@@ -501,7 +507,7 @@ def main():
                            "l2": "two alternating input/output sets of %.0f MB each (> 126 MB L2 together and singly)" % ((njv * 8 + 96) * B / 1e6),
                            "collective": ("all_gather(tip)" if gathered is not None else
                                           ("fused into the solver kernel: NVLink peer stores (%s) + 1-element all-reduce as rank barrier, "
-                                           "checked equal to all_gather_into_tensor" % a.allgather_fused) if fused is not None else "none")},
+                                           "checked equal to all_gather_into_tensor; %d destinations%s" % (a.allgather_fused, len(fused["ptrs"]), ", row-wise stores" if a.gather_rowwise else "")) if fused is not None else "none")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches}
         if a.shoot:
             it = shoot[0]["it"].cpu().numpy(); stt = shoot[0]["st"].cpu().numpy()

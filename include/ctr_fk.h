@@ -168,6 +168,8 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
  * Stores to peers are complete when the kernel is; the caller synchronises the RANKS before reading the gathered
  * buffer (a barrier).  FAST arithmetic, tip poses only.  n_out/step_out/status: local [B], nullable. */
 #define CTR_FK_FLAG_GATHER_MULTICAST 0x200u
+#define CTR_FK_FLAG_GATHER_ROWWISE   0x400u   /* one thread stores its own row (16-byte NVLink writes) instead of the
+                                                  CTA writing its 128 rows as whole lines; for comparison */
 int ctr_fk_batch_gather(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                         int32_t nsamples, uint32_t flags, void* const* tip_dst, int32_t ndst,
                         int64_t first_row, int32_t* n_out, double* step_out, int32_t* status,

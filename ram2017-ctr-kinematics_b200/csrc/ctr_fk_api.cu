@@ -254,6 +254,7 @@ int ctr_fk_batch_gather(ctr_fk_handle h, const double* jv, int64_t B, int mode, 
     a.n_out = n_out; a.step_out = step_out; a.status = status;
     for (int p = 0; p < ndst; ++p) a.gather[p] = (double*)tip_dst[p];
     a.ngather = ndst; a.gather_mc = mc ? 1 : 0; a.gather_row = first_row;
+    a.gather_rowwise = (flags & CTR_FK_FLAG_GATHER_ROWWISE) ? 1 : 0;
     int32_t* order = nullptr;
     if (mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples) {
         cudaError_t eo = make_order(h, jv, B, mode, step, nsamples, &order, st);

@@ -88,9 +88,7 @@ __device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg)
 // Register budget: 4 CTAs of 128 threads per SM (16 warps) leaves 128 registers per thread.  Measured
 // on B200 (tools/tune_tip.cu): capping registers for 20 or 24 warps/SM is 3-5 % slower — the sweep
 // is bound by FP64 issue, not by latency that more warps could hide.
-// GATHER: the pose is stored into the gathered buffer of every rank (store_tf_gather) instead of `tip` —
-// solve and all-gather in one kernel; the stores ride NVLink while the other warps keep the FP64 pipe busy.
-template <class L, bool FAST, bool GATHER = false>
+template <class L, bool FAST>
 __global__ void __launch_bounds__(kBlock, FAST ? 4 : 1)
 fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
@@ -111,24 +109,14 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
     load_jv<L>(a.jv, cfg, q);
     Ctl<L> c;
     setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-    if (c.status) {
-        write_invalid<L>(a, cfg);
-        if (GATHER) {
-            double nan12[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) nan12[j] = __longlong_as_double(0x7ff8000000000000ll);
-            store_tf_gather(a, cfg, nan12);
-        }
-        return;
-    }
+    if (c.status) { write_invalid<L>(a, cfg); return; }
 
     double tip[12];
     double alb[L::T];
     if (FAST) solve_fast<L, true>(rb, c, tip, a.alpha_base ? alb : nullptr, NoSample{});
-    else      solve_strict<L, true>(rb, c, (a.tip || GATHER) ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
+    else      solve_strict<L, true>(rb, c, a.tip ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
 
-    if (GATHER) store_tf_gather(a, cfg, tip);
-    else if (a.tip) store_tf(a.tip + cfg * 12, tip);
+    if (a.tip) store_tf(a.tip + cfg * 12, tip);
     if (a.radius) {
         if (a.soa) fill_radius<L>(rb, c, a.radius + cfg, a.B);
         else       fill_radius<L>(rb, c, a.radius + cfg * (int64_t)rb.maxs, 1);
@@ -140,6 +128,75 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
         for (int t = 0; t < L::T; ++t) a.alpha_base[cfg * L::T + t] = alb[t];
     }
     if (a.status) a.status[cfg] = 0;
+}
+
+// ---- solve + all-gather in one kernel (ctr_fk_batch_gather) --------------------------------------
+// The FAST tip solve; every pose goes to row gather_row + cfg of EVERY destination: the gathered buffers of
+// all ranks mapped into this process (NVLink peer stores), or one NVSwitch multicast address (multimem.st,
+// replicated by the switch).  The stores of one warp ride NVLink while the other warps keep the FP64 pipe busy.
+// Rows of a CTA are consecutive unless step-mode binning permuted them, so the CTA stages its 128 poses in
+// shared memory (12 KB) and writes them out as whole lines — 16-byte chunks of consecutive lanes are
+// consecutive in memory.  One thread storing its own 96-byte row makes 16-byte NVLink writes: fine with one
+// peer, 2.3x slower than no collective at all with seven (8 GPUs: 4.80 ms against 2.04 ms); kept for permuted
+// rows and as CTR_FK_FLAG_GATHER_ROWWISE for comparison.
+template <class L>
+__global__ void __launch_bounds__(kBlock, 4)
+fk_tip_gather_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
+{
+    __shared__ double2 stage[kBlock * 6];
+    int64_t i;
+    if (a.windows) {
+        const int64_t w = blockIdx.x % a.windows, r = blockIdx.x / a.windows;
+        i = w * kBinWindow + r * kBlock + threadIdx.x;
+    } else {
+        i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    }
+    const bool    active = i < a.B;
+    const int64_t cfg = active ? (a.order ? (int64_t)a.order[i] : i) : 0;
+    double tip[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) tip[j] = __longlong_as_double(0x7ff8000000000000ll);
+    if (active) {
+        double q[L::NJ];
+        load_jv<L>(a.jv, cfg, q);
+        Ctl<L> c;
+        setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
+        if (c.status) {
+            write_invalid<L>(a, cfg);                  // a.tip is null here: sample count, step, status only
+        } else {
+            solve_fast<L, true>(rb, c, tip, nullptr, NoSample{});
+            if (a.n_out) a.n_out[cfg] = c.nframes;
+            if (a.step_out) a.step_out[cfg] = c.h;
+            if (a.status) a.status[cfg] = 0;
+        }
+    }
+    if (a.order || a.gather_rowwise) {                 // uniform over the grid: no thread skips the barrier below
+        if (active) store_tf_gather(a, cfg, tip);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) stage[threadIdx.x * 6 + j] = make_double2(tip[2 * j], tip[2 * j + 1]);
+    __syncthreads();
+    const int64_t first = (int64_t)blockIdx.x * kBlock;
+    const int64_t left = a.B - first;
+    const int     nchunk = (int)(left < kBlock ? left : kBlock) * 6;
+    if (a.gather_mc) {
+        double* d = a.gather[0] + (a.gather_row + first) * 12;
+        for (int ch = threadIdx.x; ch < nchunk; ch += kBlock) {
+            const double2 v = stage[ch];
+            const unsigned long long x = (unsigned long long)__double_as_longlong(v.x), y = (unsigned long long)__double_as_longlong(v.y);
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 2 * ch),
+                         "f"(__uint_as_float((unsigned)x)), "f"(__uint_as_float((unsigned)(x >> 32))),
+                         "f"(__uint_as_float((unsigned)y)), "f"(__uint_as_float((unsigned)(y >> 32)))
+                         : "memory");
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int p = 0; p < a.ngather; ++p) {
+        double2* d = reinterpret_cast<double2*>(a.gather[p] + (a.gather_row + first) * 12);
+        for (int ch = threadIdx.x; ch < nchunk; ch += kBlock) d[ch] = stage[ch];
+    }
 }
 
 // ---- backbone kernel ---------------------------------------------------------------------------

@@ -32,6 +32,7 @@ struct FkArgs {
     double*        gather[8];
     int            ngather;     // 0: plain `tip` output
     int            gather_mc;   // destinations are multicast addresses: multimem.st
+    int            gather_rowwise; // every thread stores its own row (CTR_FK_FLAG_GATHER_ROWWISE)
     int64_t        gather_row;
 };
 

@@ -16,6 +16,7 @@ MAX_TUBES = 6
 MODE_STEP, MODE_NSAMPLE = 0, 1
 FLAG_JAC_GIVEN_POSES = 0x100
 FLAG_GATHER_MULTICAST = 0x200
+FLAG_GATHER_ROWWISE = 0x400
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1

@@ -401,9 +401,12 @@ def test_fused_gather_kernel_single_device(ctrfk, robots, engines):
         n = torch.empty(B, dtype=torch.int32, device="cuda"); n2 = torch.empty_like(n)
         eng.batch(jv, B, mode, tip=tip, n_out=n, stream=st, **kw)
         first, rows = 5, B + 11
-        bufs = [torch.full((rows, 12), -3.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+        bufs = [torch.full((rows, 12), -3.0, dtype=torch.float64, device="cuda") for _ in range(2)]     # 3000 = 23 CTAs + 56 rows
         before = ctrfk.launch_count()
         eng.batch_gather(jv, B, mode, [b.data_ptr() for b in bufs], first, n_out=n2, stream=st, **kw)
+        # the same with every thread storing its own row (the path permuted rows take anyway)
+        bufs.append(torch.full((rows, 12), -3.0, dtype=torch.float64, device="cuda"))
+        eng.batch_gather(jv, B, mode, [bufs[2].data_ptr()], first, flags=ctrfk.FLAG_GATHER_ROWWISE, stream=st, **kw)
         torch.cuda.synchronize()
         assert ctrfk.launch_count() > before and torch.equal(n, n2)
         for b in bufs:

@@ -9,6 +9,14 @@ try:
 except Exception as e:
     print('FAILED', ' '.join(sys.argv[1:]), l[:300])
 " "$@" || { echo "FAILED $@"; tail -5 gpurun_out/gather_err.log; }; }
+if [ "$2" = "peers" ]; then   # peer-store paths with the destination list replicated (emulates more peers on a small box)
+  run --allgather-fused ipc --gather-replicate 4 --gather-rowwise | tee -a gpurun_out/gather_${N}gpu_peers.txt
+  run --allgather-fused ipc --gather-replicate 4 | tee -a gpurun_out/gather_${N}gpu_peers.txt
+  run --allgather-fused ipc | tee -a gpurun_out/gather_${N}gpu_peers.txt
+  run --allgather-fused multicast | tee -a gpurun_out/gather_${N}gpu_peers.txt
+  tail -3 gpurun_out/gather_err.log
+  exit 0
+fi
 run | tee -a gpurun_out/gather_${N}gpu.txt
 run --allgather | tee -a gpurun_out/gather_${N}gpu.txt
 run --allgather-fused ipc | tee -a gpurun_out/gather_${N}gpu.txt
