@@ -21,7 +21,7 @@ def can_build():
 
 
 def build():
-    subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    subprocess.check_call(["make", "-s", "-j3", "-C", HERE, "ref"])
 
 
 def available():
