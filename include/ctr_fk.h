@@ -156,6 +156,13 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
                       int32_t nsamples, uint32_t flags,
                       double* tip, int32_t* n_out, double* step_out, int32_t* status);
 
+/* HOST pointers, WITH the backbone: backbone [B][max_samples][12] (required; the first n_out[i] frames of row i are
+ * written, getTransformSample of robot_i.h:527), radius [B][max_samples] (nullable, getRadiusSample :526), the rest
+ * as ctr_fk_batch_host.  104 * max_samples bytes per configuration come back over PCIe, which bounds this call. */
+int ctr_fk_batch_host_backbone(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
+                               int32_t nsamples, uint32_t flags, double* tip, double* backbone,
+                               double* radius, int32_t* n_out, double* step_out, int32_t* status);
+
 /* Solve + all-gather in ONE kernel (the optional all-gather of the poses over NVLink).  Every rank
  * calls this on its own slice; each thread stores its pose into row `first_row + i` of EVERY destination buffer —
  * the gathered [world * B][12] buffers of all ranks, mapped into this process (CUDA IPC: ctr_fk_peer_alloc /

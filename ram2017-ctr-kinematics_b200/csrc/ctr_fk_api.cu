@@ -383,6 +383,77 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     return ret;
 }
 
+// Host-pointer batch WITH the backbone: every frame and radius of every sample back to host memory
+// ([B][max_samples][12], [B][max_samples]).  104 * max_samples bytes per configuration cross PCIe, so the path is
+// bound by the D2H copy (26.6 KB per configuration at 256 samples: ~2e6 configurations/s at 55 GB/s); chunks are
+// sized by their staging slab (<= 256 MB), not by the kernel's wave.  Own staging allocation per call
+// (stream-ordered, from the cached pool); ctr_fk_batch_host's slabs are left alone.
+int ctr_fk_batch_host_backbone(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
+                               uint32_t flags, double* tip, double* backbone, double* radius, int32_t* n_out,
+                               double* step_out, int32_t* status)
+{
+    int rc = check_common(h, jv, B, mode, step, nsamples);
+    if (rc) return rc;
+    if (flags & CTR_FK_FLAG_SOA) { set_error("ctr_fk_batch_host_backbone: [B][max_samples][12] layout only"); return CTR_FK_E_ARG; }
+    if (!backbone) { set_error("ctr_fk_batch_host_backbone: null backbone pointer (use ctr_fk_batch_host for poses only)"); return CTR_FK_E_NULL; }
+    if (B == 0) return 0;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+
+    constexpr int NS = 3;
+    const size_t maxs = (size_t)h->rb.maxs;
+    const int    njv = h->njv;
+    const size_t per_cfg = sizeof(double) * (njv + 12 + 12 * maxs + maxs + 1) + 2 * sizeof(int32_t);
+    int64_t chunk = (int64_t)((size_t)(256u << 20) / per_cfg);
+    chunk = std::max<int64_t>(kBlock, chunk / kBlock * kBlock);
+    chunk = std::min<int64_t>(chunk, B);
+    auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t off_tip  = up256(sizeof(double) * (size_t)chunk * njv);
+    const size_t off_bb   = off_tip + up256(sizeof(double) * (size_t)chunk * 12);
+    const size_t off_rad  = off_bb + up256(sizeof(double) * (size_t)chunk * 12 * maxs);
+    const size_t off_n    = off_rad + up256(sizeof(double) * (size_t)chunk * maxs);
+    const size_t off_step = off_n + up256(sizeof(int32_t) * (size_t)chunk);
+    const size_t off_stat = off_step + up256(sizeof(double) * (size_t)chunk);
+    const size_t slab     = off_stat + up256(sizeof(int32_t) * (size_t)chunk);
+    const int nslab = (int)std::min<int64_t>(NS, (B + chunk - 1) / chunk);
+
+    char* dbuf = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&dbuf, slab * (size_t)nslab, h->streams[0]);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_batch_host_backbone: device staging allocation", e);
+    if ((e = cudaStreamSynchronize(h->streams[0])) != cudaSuccess) { cudaFreeAsync(dbuf, h->streams[0]); return cuda_fail("ctr_fk_batch_host_backbone: sync", e); }
+
+    int ret = 0;
+    int64_t done = 0;
+    for (int c = 0; done < B && ret == 0; ++c, done += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, B - done);
+        cudaStream_t st = h->streams[c % nslab];
+        char* base = dbuf + slab * (size_t)(c % nslab);
+        double*  d_jv   = (double*)base;
+        double*  d_tip  = (double*)(base + off_tip);
+        double*  d_bb   = (double*)(base + off_bb);
+        double*  d_rad  = (double*)(base + off_rad);
+        int32_t* d_n    = (int32_t*)(base + off_n);
+        double*  d_step = (double*)(base + off_step);
+        int32_t* d_stat = (int32_t*)(base + off_stat);
+        if ((e = cudaMemcpyAsync(d_jv, jv + done * njv, sizeof(double) * (size_t)nb * njv, cudaMemcpyHostToDevice, st)) != cudaSuccess) { ret = cuda_fail("H2D copy", e); break; }
+        ret = run_batch(h, d_jv, nb, mode, step, nsamples, flags, d_tip, d_bb, d_rad, d_n, d_step, nullptr, d_stat, st);
+        if (ret) break;
+        if ((e = cudaMemcpyAsync(backbone + (size_t)done * 12 * maxs, d_bb, sizeof(double) * (size_t)nb * 12 * maxs, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (radius && (e = cudaMemcpyAsync(radius + (size_t)done * maxs, d_rad, sizeof(double) * (size_t)nb * maxs, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (tip && (e = cudaMemcpyAsync(tip + done * 12, d_tip, sizeof(double) * (size_t)nb * 12, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (n_out && (e = cudaMemcpyAsync(n_out + done, d_n, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (step_out && (e = cudaMemcpyAsync(step_out + done, d_step, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+        if (status && (e = cudaMemcpyAsync(status + done, d_stat, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
+    }
+    for (int i = 0; i < nslab; ++i) {
+        e = cudaStreamSynchronize(h->streams[i]);
+        if (e != cudaSuccess && ret == 0) ret = cuda_fail("ctr_fk_batch_host_backbone: stream sync", e);
+    }
+    cudaFreeAsync(dbuf, h->streams[0]);
+    return ret;
+}
+
 int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int32_t nsamples, uint32_t flags,
                   double* tip, double* backbone, double* radius, int32_t* n_out, double* step_out,
                   double* alpha_base)

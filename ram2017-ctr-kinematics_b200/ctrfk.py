@@ -71,6 +71,7 @@ SYMBOLS = {
                                     _P, _P, _P, _P]),
     "ctr_fk_single": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int32, C.c_uint32,
                                 _P, _P, _P, _P, _P, _P]),
+    "ctr_fk_batch_host_backbone": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     "ctr_fk_batch_gather": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_uint32, _P, C.c_int32, C.c_int64,
                                       _P, _P, _P, _P]),
     "ctr_fk_peer_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P), _P]),
@@ -218,6 +219,11 @@ class Engine:
         if rc not in (0, STATUS_PHI_RANGE):
             _check(rc)
         return rc
+
+    def batch_host_backbone(self, jv, B, mode, backbone, step=0.0, nsamples=0, flags=0, tip=None, radius=None, n_out=None,
+                            step_out=None, status=None):
+        _check(load().ctr_fk_batch_host_backbone(self.handle, _ptr(jv), B, mode, step, nsamples, flags, _ptr(tip), _ptr(backbone),
+                                                 _ptr(radius), _ptr(n_out), _ptr(step_out), _ptr(status)))
 
     def batch_gather(self, jv, B, mode, dst_ptrs, first_row, step=0.0, nsamples=0, flags=0, multicast=False, n_out=None,
                      step_out=None, status=None, stream=None):

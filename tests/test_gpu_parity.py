@@ -419,6 +419,29 @@ def test_fused_gather_kernel_single_device(ctrfk, robots, engines):
         eng.batch_gather(jv, B, 1, [bufs[0].data_ptr()] * 2, 0, nsamples=10, multicast=True, stream=st)
 
 
+@pytest.mark.parametrize("maxs", [64, 256])
+def test_host_backbone_equals_device_path(ctrfk, dev, maxs):
+    """ctr_fk_batch_host_backbone (host pointers, frames + radius of every sample back over PCIe, chunked by staging
+    slab) against ctr_fk_batch on device buffers: bit-equal frames, radii, poses, counts; several chunks."""
+    d = ctrfk.desc_from_xml(ctrfk.resource("ctr_sec3_tub4.xml"), maxs)
+    eng = ctrfk.Engine(d, 0)
+    B = 45_000 if maxs == 64 else 24_000          # 256 MB slabs: 36 k / 9.6 k configurations per chunk
+    for mode, kw in ((1, dict(nsamples=maxs)), (0, dict(step=d.max_length / maxs))):
+        jv = ctrfk.sample_joints_host(d, 88, 0, B)
+        jv[17, 1] = -0.1
+        g = run_gpu(ctrfk, eng, jv, mode, backbone=True, radius=True, **kw)
+        bb = np.zeros((B, maxs, 12)); rd = np.zeros((B, maxs)); tip = np.zeros((B, 12))
+        n = np.zeros(B, np.int32); st = np.zeros(B); stat = np.zeros(B, np.int32)
+        eng.batch_host_backbone(jv, B, mode, bb, tip=tip, radius=rd, n_out=n, step_out=st, status=stat, **kw)
+        assert np.array_equal(n, g["n"]) and np.array_equal(stat, g["status"]) and stat[17] == 1
+        assert np.array_equal(st, g["step"], equal_nan=True) and np.array_equal(tip, g["tip"], equal_nan=True)
+        live = (np.arange(maxs)[None, :] < n[:, None])
+        assert np.array_equal(bb[live], g["backbone"][live]) and np.array_equal(rd[live], g["radius"][live])
+    with pytest.raises(ctrfk.CtrFkError):
+        eng.batch_host_backbone(jv, B, 1, None, nsamples=maxs)
+    eng.close()
+
+
 # ---- full-size, size-independent properties (BASELINE.json config 2: 1M configurations) --------
 
 def rz_batch(theta):
