@@ -158,6 +158,14 @@ int Robot::calcKinematicBatch(const double* jv, std::int64_t B, const std::size_
     return ctr_fk_batch_host(engine_, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, (int32_t)ns, 0u, tip, nOut, stepOut, status);
 }
 
+int Robot::calcKinematicBatch(const double* jv, std::int64_t B, const std::size_t& ns, double* tip, double* backbone,
+                              double* radius, std::int32_t* nOut)
+{
+    if (!engine_) { fool(__func__); return CTR_FK_E_NULL; }
+    return ctr_fk_batch_host_backbone(engine_, jv, B, CTR_FK_MODE_NSAMPLE, 0.0, (int32_t)ns, 0u, tip, backbone, radius, nOut,
+                                      nullptr, nullptr);
+}
+
 std::size_t Robot::getNSections() const { return engine_ ? (std::size_t)desc_.nsections : 0; }
 std::size_t Robot::getNTubes() const { return engine_ ? (std::size_t)ctr_fk_desc_ntubes(&desc_) : 0; }
 std::size_t Robot::getNJointValues() const { return engine_ ? (std::size_t)ctr_fk_desc_njoints(&desc_) : 0; }

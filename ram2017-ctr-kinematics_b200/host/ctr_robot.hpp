@@ -78,6 +78,11 @@ public:
     int calcKinematicBatch(const double* jv, std::int64_t B, const std::size_t& nSamples, double* tip,
                            std::int32_t* nOut = nullptr, double* stepOut = nullptr, std::int32_t* status = nullptr);
 
+    // ... with every sample's frame and radius: backbone [B][getMaxSamples()][12], radius [B][getMaxSamples()]
+    // (what getTransformSample / getRadiusSample return after a single call), radius nullable
+    int calcKinematicBatch(const double* jv, std::int64_t B, const std::size_t& nSamples, double* tip, double* backbone,
+                           double* radius, std::int32_t* nOut = nullptr);
+
     // ctr_robot.h:118-119; the last result is kept for getStable() (robot_i.h:535)
     bool   calcStability(const VectorJ& jv, const double& angleDiscretizationStep, const double& arcLengthStep);
     double calcDegreeStability(const VectorJ& jv, const double& angleDiscretizationStep, const double& arcLengthStep,

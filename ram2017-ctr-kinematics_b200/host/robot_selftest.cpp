@@ -80,6 +80,25 @@ int main(int argc, char** argv)
         CHECK(maxdiff(t.m, &tips[i * 12], 12) < 1e-12 && n[i] == 128);
     }
 
+    // the batch call that also returns every sample's frame and radius
+    {
+        const int Bb = 300;
+        const std::size_t ms = robot.getMaxSamples();
+        std::vector<double> bb((std::size_t)Bb * ms * 12), rad((std::size_t)Bb * ms), tp((std::size_t)Bb * 12);
+        std::vector<int32_t> nn(Bb);
+        CHECK(robot.calcKinematicBatch(batch.data(), Bb, std::size_t(100), tp.data(), bb.data(), rad.data(), nn.data()) == 0);
+        for (int i = 0; i < Bb; i += 37) {
+            VectorJ q(batch.begin() + i * 6, batch.begin() + i * 6 + 6);
+            Transform t = robot.calcKinematic(q, std::size_t(100));
+            CHECK(nn[i] == 100 && robot.getNSamples() == 100 && maxdiff(t.m, &tp[i * 12], 12) < 1e-12);
+            for (unsigned k = 0; k < 100; k += 9) {
+                Transform f = robot.getTransformSample(k);
+                CHECK(maxdiff(f.m, &bb[((std::size_t)i * ms + k) * 12], 12) < 1e-12);
+                CHECK(robot.getRadiusSample(k) == rad[(std::size_t)i * ms + k]);
+            }
+        }
+    }
+
     // copies own their engine (one arena per copy in the reference, ctr_robot.cpp:30-33)
     Robot copy(robot);
     CHECK(copy && copy.handle() != robot.handle());
