@@ -16,13 +16,18 @@
  *     -> the optional backbone / radius / n_out outputs.
  *   - copy2opencl(local_constant_mem) robot descriptor                  robot_i.h:658-686
  *     -> ctr_robot_desc (same fields, InitTrafo column-major).
- *   - calcJacobian (finite differences, NSamples form)                  robot_i.h:917-960
- *     -> ctr_fk_jacobian_batch.
+ *   - calcJacobian (finite differences), all four forms                 ctr_robot.h:121-126,
+ *                                                                       robot_i.h:901-1072
+ *     -> ctr_fk_jacobian_batch (NSamples form), ctr_fk_jacobian_batch_ex (every form).
  *   - calcStability / calcDegreeStability                               robot_i.h:756-899
  *     -> ctr_fk_stability_batch.
  *   - getRandomJointValues                                              robot_i.h:1308-1317,
  *                                                                       section_i.h:328-337
  *     -> ctr_fk_sample_joints (counter-based instead of mt19937; same distribution).
+ *   - a live CTR::Robot<double> of the reference                        ctr_robot.h:76-173
+ *     -> ctr_fk_reference_adapter.hpp (header-only): its ctr_robot_desc through the public interface.
+ * Checked against the reference's own sources, compiled with stand-in third-party headers
+ * (oracle/_ref, tests/test_reference_build.py).
  *
  * Conventions
  *   - Joint vector layout (robot_i.h:1126, section_i.h:204-209):
