@@ -252,3 +252,31 @@ def test_jacobian_config_all_forms(ctrfk, oracle, hostsim, robots, name):
                 dp, ang = util.pose_errors(o["sample"][None], smp[i][None])
                 assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
                 assert np.abs(o["jac_sample"] - jacs[i]).max() < 1e-6
+
+
+def test_fast_solver_on_degenerate_robots(ctrfk, oracle, hostsim):
+    """The FAST per-thread solver (CPU build) on the robots of test_fk_bit_equal_degenerate_robots: zero curvature
+    (the |u| < zero_tol branch with its h*|u| translation), one straight section, Poisson ratio 0, stiffness ratios
+    of 1e6, a 1 mm section — against the oracle, which equals the reference build on exactly these."""
+    rng = np.random.default_rng(78)
+    for layout in util.ALL_LAYOUTS:
+        for variant in ("all_straight", "one_straight", "nu_zero", "stiff_ratio", "short_section"):
+            d = util.random_robot(ctrfk, rng, layout, max_samples=96)
+            for s in range(d.nsections):
+                for k in range(d.sec[s].ntube):
+                    if variant == "all_straight" or (variant == "one_straight" and s == d.nsections - 1):
+                        d.sec[s].curvature[k] = 0.0
+                    if variant == "nu_zero":
+                        d.sec[s].poisson[k] = 0.0
+                    if variant == "stiff_ratio":
+                        d.sec[s].stiffness[k] = 1e3 if (s + k) % 2 == 0 else 1e-3
+                if variant == "short_section" and s == 0:
+                    d.sec[s].length = 1e-3
+            jv = ctrfk.sample_joints_host(d, 500, 0, 60)
+            for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=96)), (ctrfk.MODE_STEP, dict(step=d.max_length / 50.0))):
+                o = oracle.fk_batch(d, jv, mode, **kw)
+                for fast in (0, 1):
+                    s_ = util.hostsim_fk(hostsim, d, jv, mode, fast=fast, **kw)
+                    assert np.array_equal(s_["n"], o["n"]) and np.array_equal(s_["step"], o["step"])
+                    dp, ang = util.pose_errors(o["tip"], s_["tip"])
+                    assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT, (layout, variant, fast, dp.max(), ang.max())

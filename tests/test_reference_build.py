@@ -324,3 +324,35 @@ def test_f32_variant_next_to_the_reference_float_build(ctrfk, oracle, hostsim, r
             dp, ang = util.pose_errors(o["tip"], s["tip"])
             assert dp.max() <= 1e-4 and ang.max() <= 1e-3
             assert dp.mean() < dpr.mean() and dp.max() < dpr.max()
+
+
+def test_fk_bit_equal_degenerate_robots(ctrfk, oracle):
+    """Robots that reach the branches random parameters never do: zero curvature everywhere (the |u| ~ 0 branch of
+    curvature2Transform, robot_i.h:1245/:1264-1266, translation h*|u| instead of h — SURVEY §8g-7), one straight
+    section among curved ones, Poisson ratio 0, stiffness ratios of 1e6, a 1 mm section; every layout."""
+    rng = np.random.default_rng(77)
+    cases = 0
+    for layout in util.ALL_LAYOUTS:
+        for variant in ("all_straight", "one_straight", "nu_zero", "stiff_ratio", "short_section"):
+            d = util.random_robot(ctrfk, rng, layout, max_samples=96)
+            for s in range(d.nsections):
+                for k in range(d.sec[s].ntube):
+                    if variant == "all_straight" or (variant == "one_straight" and s == d.nsections - 1):
+                        d.sec[s].curvature[k] = 0.0
+                    if variant == "nu_zero":
+                        d.sec[s].poisson[k] = 0.0
+                    if variant == "stiff_ratio":
+                        d.sec[s].stiffness[k] = 1e3 if (s + k) % 2 == 0 else 1e-3
+                if variant == "short_section" and s == 0:
+                    d.sec[s].length = 1e-3
+            ref = ref_lib.RefRobot.from_desc(d)
+            jv = ctrfk.sample_joints_host(d, 300 + cases, 0, 120)
+            for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=96)), (ctrfk.MODE_NSAMPLE, dict(nsamples=5)),
+                             (ctrfk.MODE_STEP, dict(step=d.max_length / 50.0))):
+                o = oracle.fk_batch(d, jv, mode, backbone=True, radius=True, **kw)
+                r = ref.fk_batch(jv, mode, backbone=True, radius=True, **kw)
+                assert_same_fk(o, r, d.max_samples)
+            if variant == "all_straight":      # the quirk itself: every step contributes h*|u| = 0, the robot has no length
+                assert np.abs(r["tip"][:, 9:] - np.array(list(d.init_trafo))[9:]).max() == 0.0
+            cases += 1
+    assert cases == 70
