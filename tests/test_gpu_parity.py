@@ -442,6 +442,34 @@ def test_host_backbone_equals_device_path(ctrfk, dev, maxs):
     eng.close()
 
 
+def test_degenerate_robots(ctrfk, oracle, dev):
+    """Zero curvature everywhere (the |u| < zero_tol branch), one straight section, Poisson ratio 0, stiffness ratios of
+    1e6, a 1 mm section, over every layout: FAST and STRICT kernels against the oracle (which equals the reference
+    build on exactly these robots, tests/test_reference_build.py::test_fk_bit_equal_degenerate_robots)."""
+    rng = np.random.default_rng(78)
+    for layout in util.ALL_LAYOUTS:
+        for variant in ("all_straight", "one_straight", "nu_zero", "stiff_ratio", "short_section"):
+            d = util.random_robot(ctrfk, rng, layout, max_samples=96)
+            for s in range(d.nsections):
+                for k in range(d.sec[s].ntube):
+                    if variant == "all_straight" or (variant == "one_straight" and s == d.nsections - 1):
+                        d.sec[s].curvature[k] = 0.0
+                    if variant == "nu_zero":
+                        d.sec[s].poisson[k] = 0.0
+                    if variant == "stiff_ratio":
+                        d.sec[s].stiffness[k] = 1e3 if (s + k) % 2 == 0 else 1e-3
+                if variant == "short_section" and s == 0:
+                    d.sec[s].length = 1e-3
+            eng = ctrfk.Engine(d, 0)
+            jv = ctrfk.sample_joints_host(d, 500, 0, 256)
+            for mode, kw in ((1, dict(nsamples=96)), (0, dict(step=d.max_length / 50.0))):
+                o = oracle.fk_batch(d, jv, mode, **kw)
+                for flags in (0, 1):
+                    g = run_gpu(ctrfk, eng, jv, mode, flags=flags, **kw)
+                    assert_parity(o, g)
+            eng.close()
+
+
 # ---- full-size, size-independent properties (BASELINE.json config 2: 1M configurations) --------
 
 def rz_batch(theta):
