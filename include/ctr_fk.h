@@ -152,11 +152,18 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
                      int32_t nsamples, uint32_t flags,
                      double* tip, int32_t* n_out, double* step_out, int32_t* status, void* stream);
 
-/* Batched FK with HOST pointers (pageable or pinned).  The batch is cut into chunks that are
- * copied in, solved and copied out on rotating streams so that PCIe transfers overlap the
- * kernels.  Synchronous: returns when all outputs are in host memory.  Only tip / n_out /
- * step_out / status are offered here (backbone output is 26 KB per configuration and is meant to
- * stay on the device). */
+/* Batched FK with HOST pointers (pageable or pinned).  Synchronous: returns when all outputs are in
+ * host memory.  Two forms, chosen per call:
+ *   - zero-copy (every buffer page-locked — cudaHostAlloc / cudaHostRegister / torch pin_memory() — and
+ *     16-byte aligned, FAST arithmetic): ONE kernel launch reads the joint vectors from and writes the
+ *     poses to host memory directly, whole lines at a time; PCIe runs in both directions under the
+ *     arithmetic for the whole batch.  CTR_FK_FLAG_HOST_STAGED (or CTRFK_HOST_ZEROCOPY=0 in the
+ *     environment at ctr_fk_create) selects the other form.
+ *   - staged (pageable memory, STRICT): the batch is cut into chunks that are copied in, solved and
+ *     copied out on rotating streams so that PCIe transfers overlap the kernels.
+ * Only tip / n_out / step_out / status are offered here (backbone output is 26 KB per configuration
+ * and is meant to stay on the device; see ctr_fk_batch_host_backbone). */
+#define CTR_FK_FLAG_HOST_STAGED 0x800u
 int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                       int32_t nsamples, uint32_t flags,
                       double* tip, int32_t* n_out, double* step_out, int32_t* status);
@@ -316,6 +323,9 @@ int ctr_fk_count_samples_host(const ctr_robot_desc* desc, const double* jv, int6
 /* FP64 FMA-pipe peak probe: runs independent DFMA chains on every SM for `iters` iterations on
  * `stream` and returns the number of flops issued (2 per DFMA per lane).  Time it with events. */
 int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* stream);
+/* The same for the FP32 FMA pipe in its packed form (fma.rn.f32x2, SASS FFMA2 — what the FP32 variant's
+ * solver issues): 4 flops per instruction per lane. */
+int ctr_fk_fp32_probe(int device, int32_t iters, double* flops_issued, void* stream);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t ctr_fk_launch_count(void);
 

@@ -28,6 +28,7 @@ struct ctr_fk_engine {
     static constexpr int kStreams = 8;      // created; ctr_fk_batch_host uses host_streams of them
     int            host_streams; // pipeline depth of the host-pointer path (4; CTRFK_HOST_STREAMS overrides, for tuning)
     int            host_chunk_waves; // chunk size of the host-pointer path in waves of the tip kernel (1; CTRFK_HOST_CHUNK_WAVES)
+    int            host_zero_copy;   // page-locked host buffers are accessed by the kernel directly (1; CTRFK_HOST_ZEROCOPY=0 disables)
     cudaStream_t   streams[kStreams];
     std::mutex     host_mu;      // serialises ctr_fk_batch_host / ctr_fk_single calls on one handle
     char*          single_buf;   // device scratch of ctr_fk_single (lazily allocated)
@@ -95,7 +96,7 @@ int check_common(ctr_fk_handle h, const double* jv, int64_t B, int mode, double 
     return 0;
 }
 
-// Build `order` (longest sweeps first inside every window of 16384 configurations) for a step-mode
+// Build `order` (longest sweeps first inside every window of kBinWindow = 4096 configurations) for a step-mode
 // batch.  One stream-ordered allocation, freed by the caller after the solver launch.
 cudaError_t make_order(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t ns,
                        int32_t** order_out, cudaStream_t st)
@@ -107,6 +108,22 @@ cudaError_t make_order(ctr_fk_handle h, const double* jv, int64_t B, int mode, d
     if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
     *order_out = order;
     return cudaSuccess;
+}
+
+// Device-side alias of a HOST range when the whole range is page-locked and mapped into the device's address
+// space (cudaHostAlloc / cudaHostRegister, torch pin_memory()): kernels can then read and write it over PCIe
+// directly.  nullptr for pageable memory (or a null pointer).
+void* device_alias(const void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return nullptr;
+    cudaPointerAttributes lo, hi;
+    if (cudaPointerGetAttributes(&lo, p) != cudaSuccess || cudaPointerGetAttributes(&hi, (const char*)p + bytes - 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    if (lo.type != cudaMemoryTypeHost || hi.type != cudaMemoryTypeHost || !lo.devicePointer || !hi.devicePointer) return nullptr;
+    if ((const char*)hi.devicePointer - (const char*)lo.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;
+    return lo.devicePointer;
 }
 
 int run_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
@@ -180,6 +197,8 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
     h->host_streams = 4;
     h->host_chunk_waves = 1;
     if (const char* ev = std::getenv("CTRFK_HOST_STREAMS")) { const int v = std::atoi(ev); if (v >= 1 && v <= ctr_fk_engine::kStreams) h->host_streams = v; }
+    h->host_zero_copy = 1;
+    if (const char* ev = std::getenv("CTRFK_HOST_ZEROCOPY")) h->host_zero_copy = std::atoi(ev) != 0;
     if (const char* ev = std::getenv("CTRFK_HOST_CHUNK_WAVES")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) h->host_chunk_waves = v; }
     h->single_buf = nullptr;
     h->stage_buf = nullptr;
@@ -243,7 +262,7 @@ int ctr_fk_batch_gather(ctr_fk_handle h, const double* jv, int64_t B, int mode, 
     }
     for (int p = 0; p < ndst; ++p)
         if (!tip_dst[p] || !aligned16(tip_dst[p])) { set_error("ctr_fk_batch_gather: destination %d null or not 16-byte aligned", p); return CTR_FK_E_ARG; }
-    if ((rc = check_align(h, jv, nullptr, nullptr))) return rc;
+    if (!aligned16(jv)) { set_error("ctr_fk_batch_gather: the joint-vector buffer must be 16-byte aligned"); return CTR_FK_E_ARG; }
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
@@ -326,6 +345,32 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     std::lock_guard<std::mutex> lock(h->host_mu);
+
+    // ---- zero-copy form: page-locked host buffers are read and written by the solver kernel itself -------------
+    // One launch over the whole batch: every CTA fetches its joint vectors from host memory as whole lines, solves,
+    // stages its 128 poses in shared memory and writes them to host memory as whole lines (fk_tip_gather_kernel
+    // with the host buffer as its one destination).  No staging slabs, no chunk pipeline to fill and drain, reads
+    // and writes share the PCIe link in both directions for the whole run, and the transfers of one warp overlap
+    // the arithmetic of the other fifteen on its SM.  Taken when every buffer passed in is page-locked (pinned or
+    // registered) and 16-byte aligned, and the arithmetic is FAST; pageable memory, STRICT and
+    // CTR_FK_FLAG_HOST_STAGED take the chunked copy pipeline below.
+    if (h->host_zero_copy && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED)) && tip && aligned16(jv) && aligned16(tip)) {
+        const size_t nb = (size_t)B;
+        double*  z_jv   = (double*)device_alias(jv, sizeof(double) * nb * h->njv);
+        double*  z_tip  = (double*)device_alias(tip, sizeof(double) * nb * 12);
+        int32_t* z_n    = n_out ? (int32_t*)device_alias(n_out, sizeof(int32_t) * nb) : nullptr;
+        double*  z_step = step_out ? (double*)device_alias(step_out, sizeof(double) * nb) : nullptr;
+        int32_t* z_stat = status ? (int32_t*)device_alias(status, sizeof(int32_t) * nb) : nullptr;
+        if (z_jv && z_tip && (!n_out || z_n) && (!step_out || z_step) && (!status || z_stat)) {
+            void* dst[1] = {z_tip};
+            cudaStream_t st = h->streams[0];
+            rc = ctr_fk_batch_gather(h, z_jv, B, mode, step, nsamples, flags, dst, 1, 0, z_n, z_step, z_stat, st);
+            cudaError_t es = cudaStreamSynchronize(st);
+            if (rc) return rc;
+            if (es != cudaSuccess) return cuda_fail("ctr_fk_batch_host (zero-copy): sync", es);
+            return 0;
+        }
+    }
 
     const int NS = h->host_streams;
     // one chunk = one full wave of the tip kernel (4 CTAs of kBlock threads per SM): a chunk that
@@ -754,7 +799,12 @@ int ctr_fk_sample_joints(ctr_fk_handle h, uint64_t seed, int64_t first_config, i
     return ctr_fk_sample_joints_scaled(h, seed, first_config, B, CTR_FK_SCALE_NONE, 1.0, 1.0, 0, jv, stream);
 }
 
-int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* stream)
+static int peak_probe(int device, int32_t iters, double* flops_issued, void* stream, bool f32);
+
+int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* stream) { return peak_probe(device, iters, flops_issued, stream, false); }
+int ctr_fk_fp32_probe(int device, int32_t iters, double* flops_issued, void* stream) { return peak_probe(device, iters, flops_issued, stream, true); }
+
+static int peak_probe(int device, int32_t iters, double* flops_issued, void* stream, bool f32)
 {
     if (iters < 1) { set_error("iters must be >= 1"); return CTR_FK_E_ARG; }
     DeviceGuard g(device);
@@ -762,17 +812,20 @@ int ctr_fk_fp64_probe(int device, int32_t iters, double* flops_issued, void* str
     int sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return cuda_fail("cudaDeviceGetAttribute", e);
-    static double* sink = nullptr;   // one 8-byte device word per process; never written
+    static double* sinks[64] = {nullptr};   // one 8-byte word per device, never written
     static std::mutex mu;
+    double* sink = nullptr;
     {
         std::lock_guard<std::mutex> lk(mu);
-        if (!sink && (e = cudaMalloc((void**)&sink, sizeof(double))) != cudaSuccess) return cuda_fail("cudaMalloc", e);
+        if (device < 0 || device >= 64) { set_error("device index out of range"); return CTR_FK_E_ARG; }
+        if (!sinks[device] && (e = cudaMalloc((void**)&sinks[device], sizeof(double))) != cudaSuccess) return cuda_fail("cudaMalloc", e);
+        sink = sinks[device];
     }
     const int blocks = sms * 8;
-    e = launch_fp64_probe(iters, blocks, sink, (cudaStream_t)stream);
+    e = f32 ? launch_fp32x2_probe(iters, blocks, sink, (cudaStream_t)stream) : launch_fp64_probe(iters, blocks, sink, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail("probe kernel launch", e);
     if (flops_issued)
-        *flops_issued = 2.0 * (double)blocks * kProbeThreads * kProbeChains * 8.0 * (double)iters;
+        *flops_issued = (f32 ? 4.0 : 2.0) * (double)blocks * kProbeThreads * kProbeChains * 8.0 * (double)iters;
     return 0;
 }
 

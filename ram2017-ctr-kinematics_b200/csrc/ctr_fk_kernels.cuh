@@ -156,9 +156,31 @@ fk_tip_gather_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ 
     double tip[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) tip[j] = __longlong_as_double(0x7ff8000000000000ll);
-    if (active) {
-        double q[L::NJ];
+    double q[L::NJ];
+    if (!a.order) {
+        // The CTA's joint vectors are one contiguous run of kBlock * NJ doubles: fetch it as whole lines
+        // (consecutive lanes, consecutive 16-byte chunks) and hand every thread its row through shared memory.
+        // For device memory this equals the per-thread loads; when `jv` is mapped host memory (the zero-copy
+        // form of ctr_fk_batch_host) every byte crosses PCIe exactly once, in full read requests.
+        static_assert(L::NJ * 8 <= 6 * 16, "the pose stage holds a CTA's joint vectors");
+        const int64_t first = (int64_t)blockIdx.x * kBlock;
+        const int64_t left  = a.B - first;
+        const int     ndbl  = (int)(left < kBlock ? left : kBlock) * L::NJ;       // doubles of this CTA
+        const double* src   = a.jv + first * L::NJ;                              // 16-byte aligned: kBlock * NJ is even
+        double*       sj    = reinterpret_cast<double*>(stage);
+        for (int ch = threadIdx.x; 2 * ch + 1 < ndbl; ch += kBlock)
+            reinterpret_cast<double2*>(sj)[ch] = __ldg(reinterpret_cast<const double2*>(src) + ch);
+        if ((ndbl & 1) && threadIdx.x == 0) sj[ndbl - 1] = __ldg(src + ndbl - 1);
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < L::NJ; ++j) q[j] = sj[threadIdx.x * L::NJ + j];
+        }
+        __syncthreads();                              // the stage is reused for the poses below
+    } else if (active) {
         load_jv<L>(a.jv, cfg, q);
+    }
+    if (active) {
         Ctl<L> c;
         setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
         if (c.status) {

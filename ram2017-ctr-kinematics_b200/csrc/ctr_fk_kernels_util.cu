@@ -167,6 +167,41 @@ fp64_probe_kernel(int iters, double* sink)
     if (s == 12345.678) sink[0] = s;   // never true; keeps the chains alive
 }
 
+// ---- FP32 FMA-pipe probe, packed form ------------------------------------------------------------
+// The FP32 variant's solver issues fma.rn.f32x2 (SASS FFMA2: one instruction, two lanes of a 64-bit register
+// pair), so its roofline denominator is the rate at which independent FFMA2 chains retire on every SM.
+// flops = threads * chains * 8 * iters * 4 (two FMAs of two flops per instruction).
+__global__ void __launch_bounds__(kProbeThreads)
+fp32x2_probe_kernel(int iters, double* sink)
+{
+    unsigned long long v[kProbeChains];
+#pragma unroll
+    for (int j = 0; j < kProbeChains; ++j) {
+        const float f = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+        v[j] = ((unsigned long long)__float_as_uint(f) << 32) | __float_as_uint(f);
+    }
+    const unsigned long long a = ((unsigned long long)__float_as_uint(1.0000001f) << 32) | __float_as_uint(0.9999999f);
+    const unsigned long long b = ((unsigned long long)__float_as_uint(1e-7f) << 32) | __float_as_uint(-1e-7f);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int j = 0; j < kProbeChains; ++j) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[j]) : "l"(a), "l"(b));
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < kProbeChains; ++j) s ^= v[j];
+    if (s == 0x123456789abcdefull) sink[0] = 1.0;   // never true; keeps the chains alive
+}
+
+cudaError_t launch_fp32x2_probe(int iters, int blocks, double* sink, cudaStream_t st)
+{
+    fp32x2_probe_kernel<<<blocks, kProbeThreads, 0, st>>>(iters, sink);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fp64_probe(int iters, int blocks, double* sink, cudaStream_t st)
 {
     fp64_probe_kernel<<<blocks, kProbeThreads, 0, st>>>(iters, sink);

@@ -95,7 +95,7 @@ cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, int s
 // base-angle shooting solve: persistent kernel with a ticket queue (grid sized to the device)
 cudaError_t launch_shoot(int key, const KRobot& rb, const ShootArgs& a, int sm_count, cudaStream_t st);
 
-// step-mode binning: `order` = every window of 16384 consecutive configurations counting-sorted by
+// step-mode binning: `order` = every window of kBinWindow = 4096 consecutive configurations counting-sorted by
 // sample count, longest sweeps first (ctr_fk_kernels_util.cu)
 cudaError_t launch_bin_local(int key, const KRobot& rb, const double* jv, int64_t B, int mode, double step,
                              int nsamples, int32_t* order, cudaStream_t st);
@@ -112,6 +112,7 @@ struct SamplerArgs {
 };
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_fp64_probe(int iters, int blocks, double* sink, cudaStream_t st);
+cudaError_t launch_fp32x2_probe(int iters, int blocks, double* sink, cudaStream_t st);
 constexpr int kProbeThreads = 256;
 constexpr int kProbeChains  = 8;
 

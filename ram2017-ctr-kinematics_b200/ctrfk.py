@@ -17,6 +17,7 @@ MODE_STEP, MODE_NSAMPLE = 0, 1
 FLAG_JAC_GIVEN_POSES = 0x100
 FLAG_GATHER_MULTICAST = 0x200
 FLAG_GATHER_ROWWISE = 0x400
+FLAG_HOST_STAGED = 0x800
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
@@ -97,6 +98,7 @@ SYMBOLS = {
     "ctr_fk_count_samples_host": (C.c_int, [C.POINTER(RobotDesc), _P, C.c_int64, C.c_int, C.c_double,
                                             C.c_int32, _P]),
     "ctr_fk_fp64_probe": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_double), _P]),
+    "ctr_fk_fp32_probe": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_double), _P]),
     "ctr_fk_launch_count": (C.c_int64, []),
     "ctr_fk_last_error": (C.c_char_p, []),
     "ctr_fk_version": (C.c_char_p, []),
@@ -308,6 +310,12 @@ def count_samples_host(desc, jv, mode, step=0.0, nsamples=0):
 def fp64_probe(device, iters, stream=None):
     flops = C.c_double(0.0)
     _check(load().ctr_fk_fp64_probe(device, iters, C.byref(flops), stream))
+    return flops.value
+
+
+def fp32_probe(device, iters, stream=None):
+    flops = C.c_double(0.0)
+    _check(load().ctr_fk_fp32_probe(device, iters, C.byref(flops), stream))
     return flops.value
 
 
