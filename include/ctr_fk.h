@@ -168,6 +168,17 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
                       int32_t nsamples, uint32_t flags,
                       double* tip, int32_t* n_out, double* step_out, int32_t* status);
 
+/* Page-locked, device-mapped host buffers for the calls above, placed for the engine's GPU: the pages are faulted in
+ * while the calling thread is bound to the CPUs local to the GPU's PCIe root, so they land on the GPU's NUMA node
+ * (on a multi-socket host a buffer on the far socket sends every transfer across the inter-socket link as well).
+ * CTR_FK_HOST_WRITE_COMBINED: for buffers the host only ever writes (joint vectors); host reads of such memory are
+ * slow.  ctr_fk_host_local_cpus writes those CPUs as a cpulist string ("0-15,32-47"; empty if unknown) for callers
+ * that want to bind their own worker threads. */
+#define CTR_FK_HOST_WRITE_COMBINED 1u
+int ctr_fk_host_alloc(ctr_fk_handle h, size_t bytes, uint32_t flags, void** ptr);
+int ctr_fk_host_free(ctr_fk_handle h, void* ptr);
+int ctr_fk_host_local_cpus(ctr_fk_handle h, char* buf, size_t len);
+
 /* HOST pointers, WITH the backbone: backbone [B][max_samples][12] (required; the first n_out[i] frames of row i are
  * written, getTransformSample of robot_i.h:527), radius [B][max_samples] (nullable, getRadiusSample :526), the rest
  * as ctr_fk_batch_host.  104 * max_samples bytes per configuration come back over PCIe, which bounds this call. */

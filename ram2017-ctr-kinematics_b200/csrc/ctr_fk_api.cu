@@ -2,7 +2,11 @@
 // No CPU fallback anywhere in this file: if a device call fails the CUDA error code is returned.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -354,7 +358,11 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     // the arithmetic of the other fifteen on its SM.  Taken when every buffer passed in is page-locked (pinned or
     // registered) and 16-byte aligned, and the arithmetic is FAST; pageable memory, STRICT and
     // CTR_FK_FLAG_HOST_STAGED take the chunked copy pipeline below.
-    if (h->host_zero_copy && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED)) && tip && aligned16(jv) && aligned16(tip)) {
+    // Step-mode batches that get binned stay on the staged form: binning permutes the rows of a CTA, and permuted
+    // 96-byte rows would cross PCIe as scattered 16-byte writes (and the binning pass would read the joint vectors
+    // over PCIe a second time).
+    const bool binned = mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples;
+    if (h->host_zero_copy && !binned && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED)) && tip && aligned16(jv) && aligned16(tip)) {
         const size_t nb = (size_t)B;
         double*  z_jv   = (double*)device_alias(jv, sizeof(double) * nb * h->njv);
         double*  z_tip  = (double*)device_alias(tip, sizeof(double) * nb * 12);
@@ -497,6 +505,96 @@ int ctr_fk_batch_host_backbone(ctr_fk_handle h, const double* jv, int64_t B, int
     }
     cudaFreeAsync(dbuf, h->streams[0]);
     return ret;
+}
+
+// ---- page-locked host buffers placed for the engine's GPU ------------------------------------------------------
+// The zero-copy form of ctr_fk_batch_host moves every byte over the GPU's PCIe link straight from / into the caller's
+// pages, so WHERE those pages live matters on a multi-socket host: a buffer on the other socket makes every transfer
+// cross the inter-socket link too, and eight ranks doing so share it.  ctr_fk_host_alloc binds the calling thread to
+// the CPUs local to the GPU's PCIe root (sysfs local_cpulist of the device's bus id) while cudaHostAlloc faults the
+// pages in — first touch puts them on that NUMA node — and restores the thread's affinity afterwards.
+namespace {
+bool gpu_local_cpus(int device, cpu_set_t* out)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return false;
+    char line[4096] = {0};
+    const bool got = std::fgets(line, sizeof line, f) != nullptr;
+    std::fclose(f);
+    if (!got) return false;
+    CPU_ZERO(out);
+    int n = 0;
+    for (char* p = line; *p && *p != '\n';) {             // "0-15,32-47"
+        char* end = nullptr;
+        long a = std::strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') { b = std::strtol(p + 1, &end, 10); p = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, out); ++n; }
+        if (*p == ',') ++p;
+    }
+    return n > 0;
+}
+}  // namespace
+
+int ctr_fk_host_alloc(ctr_fk_handle h, size_t bytes, uint32_t flags, void** ptr)
+{
+    if (!h || !ptr) { set_error("ctr_fk_host_alloc: null argument"); return CTR_FK_E_NULL; }
+    *ptr = nullptr;
+    DeviceGuard g(h->device);
+    if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
+    cpu_set_t before, local, both;
+    bool bound = false;
+    if (sched_getaffinity(0, sizeof before, &before) == 0 && gpu_local_cpus(h->device, &local)) {
+        CPU_AND(&both, &before, &local);
+        if (CPU_COUNT(&both) > 0 && !CPU_EQUAL(&both, &before)) bound = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    unsigned int fl = cudaHostAllocMapped | cudaHostAllocPortable;
+    if (flags & CTR_FK_HOST_WRITE_COMBINED) fl |= cudaHostAllocWriteCombined;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 16, fl);
+    if (bound) sched_setaffinity(0, sizeof before, &before);
+    if (e != cudaSuccess) { *ptr = nullptr; return cuda_fail("ctr_fk_host_alloc: cudaHostAlloc", e); }
+    return 0;
+}
+
+int ctr_fk_host_free(ctr_fk_handle h, void* ptr)
+{
+    if (!h) { set_error("null engine handle"); return CTR_FK_E_NULL; }
+    if (!ptr) return 0;
+    DeviceGuard g(h->device);
+    const cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return cuda_fail("ctr_fk_host_free", e);
+    return 0;
+}
+
+// CPUs local to the engine's GPU as a cpulist string ("0-15,32-47"); empty when the platform does not say.
+int ctr_fk_host_local_cpus(ctr_fk_handle h, char* buf, size_t len)
+{
+    if (!h || !buf || len < 2) { set_error("ctr_fk_host_local_cpus: null argument"); return CTR_FK_E_NULL; }
+    buf[0] = 0;
+    cpu_set_t local;
+    if (!gpu_local_cpus(h->device, &local)) return 0;
+    size_t off = 0;
+    for (int c = 0; c < CPU_SETSIZE;) {
+        if (!CPU_ISSET(c, &local)) { ++c; continue; }
+        int e = c;
+        while (e + 1 < CPU_SETSIZE && CPU_ISSET(e + 1, &local)) ++e;
+        char piece[32];
+        if (e > c) std::snprintf(piece, sizeof piece, "%s%d-%d", off ? "," : "", c, e);
+        else       std::snprintf(piece, sizeof piece, "%s%d", off ? "," : "", c);
+        const size_t n = std::strlen(piece);
+        if (off + n + 1 > len) break;
+        std::memcpy(buf + off, piece, n + 1);
+        off += n;
+        c = e + 1;
+    }
+    return 0;
 }
 
 int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int32_t nsamples, uint32_t flags,

@@ -18,6 +18,7 @@ FLAG_JAC_GIVEN_POSES = 0x100
 FLAG_GATHER_MULTICAST = 0x200
 FLAG_GATHER_ROWWISE = 0x400
 FLAG_HOST_STAGED = 0x800
+HOST_WRITE_COMBINED = 1
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
@@ -97,6 +98,9 @@ SYMBOLS = {
     "ctr_fk_sample_joints_host": (C.c_int, [C.POINTER(RobotDesc), C.c_uint64, C.c_int64, C.c_int64, _P]),
     "ctr_fk_count_samples_host": (C.c_int, [C.POINTER(RobotDesc), _P, C.c_int64, C.c_int, C.c_double,
                                             C.c_int32, _P]),
+    "ctr_fk_host_alloc": (C.c_int, [_P, C.c_size_t, C.c_uint32, C.POINTER(_P)]),
+    "ctr_fk_host_free": (C.c_int, [_P, _P]),
+    "ctr_fk_host_local_cpus": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "ctr_fk_fp64_probe": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_double), _P]),
     "ctr_fk_fp32_probe": (C.c_int, [C.c_int, C.c_int32, C.POINTER(C.c_double), _P]),
     "ctr_fk_launch_count": (C.c_int64, []),
@@ -212,6 +216,29 @@ class Engine:
                    status=None):
         _check(load().ctr_fk_batch_host(self.handle, _ptr(jv), B, mode, step, nsamples, flags, _ptr(tip),
                                         _ptr(n_out), _ptr(step_out), _ptr(status)))
+
+    def host_alloc(self, nbytes, write_combined=False):
+        """Page-locked, device-mapped host memory on the GPU's NUMA node (ctr_fk_host_alloc); returns the address."""
+        p = _P()
+        _check(load().ctr_fk_host_alloc(self.handle, nbytes, HOST_WRITE_COMBINED if write_combined else 0, C.byref(p)))
+        return p.value
+
+    def host_free(self, ptr):
+        _check(load().ctr_fk_host_free(self.handle, ptr))
+
+    def host_array(self, shape, dtype="float64", write_combined=False):
+        """numpy view of a fresh ctr_fk_host_alloc buffer (freed when the view's base dies or by host_free)."""
+        import numpy as np
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self.host_alloc(max(n, 16), write_combined)
+        buf = (C.c_ubyte * max(n, 16)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr, ptr
+
+    def host_local_cpus(self):
+        buf = C.create_string_buffer(4096)
+        _check(load().ctr_fk_host_local_cpus(self.handle, buf, 4096))
+        return buf.value.decode()
 
     def single(self, jv, mode, step=0.0, nsamples=0, flags=0, tip=None, backbone=None, radius=None,
                n_out=None, step_out=None, alpha_base=None):

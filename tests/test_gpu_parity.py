@@ -296,6 +296,57 @@ def test_host_pointer_batch_and_single(ctrfk, oracle, robots, engines):
         assert np.array_equal(t1, bb[r["n"] - 1])
 
 
+@pytest.mark.parametrize("name", ["ctr_sec2_tub3.xml", "ctr_sec3_tub3.xml"])      # even and odd joint counts
+def test_host_pointer_zero_copy_form(ctrfk, oracle, robots, engines, name):
+    """ctr_fk_batch_host with page-locked buffers: ONE kernel reads the joint vectors from and writes every output to
+    host memory directly.  Buffers from ctr_fk_host_alloc (NUMA-local, mapped; one write-combined) and from torch's
+    pin_memory(); a batch whose last CTA is partial; an invalid configuration; all outputs.  Bit-equal to the staged
+    form (CTR_FK_FLAG_HOST_STAGED) and to the device-pointer call, launches counted: 1 against one per chunk."""
+    d = robots[name]
+    eng = engines[name]
+    B = 200_000 + 77
+    jv_np = ctrfk.sample_joints_host(d, util.SEEDS[name] + 5, 0, B)
+    jv_np[1234, 1] = -1e-3                                        # Phi out of range: NaN pose, status 1
+    jv, p_jv = eng.host_array((B, d.njoints), write_combined=True)
+    tip, p_tip = eng.host_array((B, 12))
+    n, p_n = eng.host_array((B,), dtype="int32")
+    st, p_st = eng.host_array((B,))
+    status, p_status = eng.host_array((B,), dtype="int32")
+    jv[...] = jv_np
+    tip[...] = 7.0
+    assert isinstance(eng.host_local_cpus(), str)
+    for mode, kw in ((1, dict(nsamples=96)), (0, dict(step=d.max_length / 256.0, flags=ctrfk.FLAG_NO_BINNING))):
+        l0 = ctrfk.launch_count()
+        eng.batch_host(jv, B, mode, tip=tip, n_out=n, step_out=st, status=status, **kw)
+        assert ctrfk.launch_count() - l0 == 1, "zero-copy form is one launch"
+        kw2 = dict(kw); kw2["flags"] = kw.get("flags", 0) | ctrfk.FLAG_HOST_STAGED
+        tip2 = np.zeros((B, 12)); n2 = np.zeros(B, np.int32); st2 = np.zeros(B); status2 = np.zeros(B, np.int32)
+        l0 = ctrfk.launch_count()
+        eng.batch_host(jv_np, B, mode, tip=tip2, n_out=n2, step_out=st2, status=status2, **kw2)
+        assert ctrfk.launch_count() - l0 > 1, "staged form is one launch per chunk"
+        assert np.array_equal(tip, tip2, equal_nan=True) and np.array_equal(n, n2)
+        assert np.array_equal(st, st2, equal_nan=True) and np.array_equal(status, status2)
+        assert status[1234] == 1 and np.isnan(tip[1234]).all() and status.sum() == 1
+        g = run_gpu(ctrfk, eng, jv_np, mode, **kw)
+        assert np.array_equal(tip, g["tip"], equal_nan=True) and np.array_equal(n, g["n"])
+        ok = np.arange(B) != 1234
+        o = oracle.fk_batch(d, jv_np[:5000], mode, **{k: v for k, v in kw.items() if k != "flags"})
+        dp, ang = util.pose_errors(o["tip"][ok[:5000]], tip[:5000][ok[:5000]])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT
+    # torch-pinned buffers take the same path; a binned step-mode batch and STRICT fall back to the staged form
+    jvp = torch.from_numpy(jv_np).pin_memory(); tipp = torch.zeros(B, 12, dtype=torch.float64).pin_memory()
+    l0 = ctrfk.launch_count()
+    eng.batch_host(jvp, B, 1, nsamples=96, tip=tipp)
+    assert ctrfk.launch_count() - l0 == 1
+    eng.batch_host(jv, B, 1, nsamples=96, tip=tip)
+    assert np.array_equal(tipp.numpy(), tip, equal_nan=True)
+    l0 = ctrfk.launch_count()
+    eng.batch_host(jvp, B, 0, step=d.max_length / 256.0, tip=tipp)
+    assert ctrfk.launch_count() - l0 > 1
+    for p in (p_jv, p_tip, p_n, p_st, p_status):
+        eng.host_free(p)
+
+
 def test_device_sampler_equals_host_sampler(ctrfk, robots, engines):
     st = torch.cuda.current_stream().cuda_stream
     for name in util.ROBOT_FILES:
