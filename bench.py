@@ -645,18 +645,31 @@ def run_e2e(ctx, a, w, live):
             d_jv.copy_(h_jv_t, non_blocking=True)
         with torch.cuda.stream(s_out):
             h_tip_t.copy_(d_tip, non_blocking=True)
-    both_ways()
-    barrier(ctx)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        both_ways()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    def h2d_only():
+        with torch.cuda.stream(s_in):
+            d_jv.copy_(h_jv_t, non_blocking=True)
+
+    def d2h_only():
+        with torch.cuda.stream(s_out):
+            h_tip_t.copy_(d_tip, non_blocking=True)
+
+    def all_ranks_rate(fn, nbytes):
+        """aggregate GB/s of `fn` run `reps` times by every rank at once (total bytes / slowest rank's time)"""
+        fn()
+        barrier(ctx)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * nbytes * reps / float(tt.item()) / 1e9
     step_bytes = B * (njv * 8 + 96)
-    agg_gbs = world * step_bytes * reps / float(tt.item()) / 1e9
+    agg_gbs = all_ranks_rate(both_ways, step_bytes)
+    agg_h2d = all_ranks_rate(h2d_only, B * njv * 8)
+    agg_d2h = all_ranks_rate(d2h_only, B * 96)
     ceiling = agg_gbs * 1e9 / (njv * 8 + 96)
 
     # (2) the call itself, host buffers placed by ctr_fk_host_alloc (page-locked, mapped, on the GPU's NUMA node)
@@ -691,7 +704,7 @@ def run_e2e(ctx, a, w, live):
                            (", joint vectors write-combined" if a.e2e_wc else ""),
            "cpu_binding": ("process bound to GPU-local CPUs %s" % bound[1]) if bound else "none needed (the GPU's local CPU list covers the process's CPUs, or is unknown)",
            "pcie_measured": single,
-           "pcie_aggregate": {"GBs": agg_gbs, "ranks": world, "bytes_per_rank_per_rep": step_bytes, "reps": reps,
+           "pcie_aggregate": {"GBs": agg_gbs, "h2d_only_GBs": agg_h2d, "d2h_only_GBs": agg_d2h, "ranks": world, "bytes_per_rank_per_rep": step_bytes, "reps": reps,
                               "how": "after a barrier every rank copies one step's bytes both ways at once (H2D %d MB and D2H %d MB on two "
                                      "streams, pinned memory), %d times; total bytes of all ranks / slowest rank's time" % (
                                          B * njv * 8 // 1000000, B * 96 // 1000000, reps),

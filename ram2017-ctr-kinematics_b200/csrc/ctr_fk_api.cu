@@ -381,9 +381,9 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     }
 
     const int NS = h->host_streams;
-    // one chunk = one full wave of the tip kernel (4 CTAs of kBlock threads per SM): a chunk that
+    // one chunk = one full wave of the tip kernel (3 or 4 CTAs of kBlock threads per SM): a chunk that
     // fills only part of the resident slots would pay a whole wave time for less work
-    const int64_t wave = (int64_t)h->sm_count * 4 * kBlock * h->host_chunk_waves;
+    const int64_t wave = (int64_t)h->sm_count * tip_blocks_per_sm(h->ntubes, h->desc.nsections) * kBlock * h->host_chunk_waves;
     const int64_t chunk = std::min<int64_t>(wave > 0 ? wave : kHostChunk, B);
     const int njv = h->njv;
     // one slab per stream: jv | tip | n_out | step_out | status

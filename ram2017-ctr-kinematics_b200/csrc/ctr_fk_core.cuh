@@ -28,6 +28,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define CTR_HD __host__ __device__ __forceinline__
 #else
@@ -660,10 +662,17 @@ template <bool EMIT, bool HOT> struct EmitPending { template <class F> static CT
 template <> struct EmitPending<true, true>  { template <class F> static CTR_HD void call(F& f) { f.emit_hot(); } };
 template <> struct EmitPending<true, false> { template <class F> static CTR_HD void call(F& f) { f.emit_generic(); } };
 
-template <class L, bool WANT_TIP, class OnSample>
+// HALF: the innermost tube's angle is carried as the sin/cos of its HALF (rotated by d/2 per step) and the full-angle
+// pair the sweep needs follows by the double-angle formulas; the functor receives the half-angle pair of every sample
+// through set_half() — what a frame emitter needs for the quaternion of Rz(alpha_k + theta) (PendingFrameEmitter).
+struct NoHalf { template <class F> static CTR_HD void set(F&, double, double) {} };
+struct PassHalf { template <class F> static CTR_HD void set(F& f, double s, double c) { f.set_half(s, c); } };
+
+template <class L, bool WANT_TIP, class OnSample, bool HALF = false>
 struct FastSweep {
     static constexpr int  S = L::S, T = L::T;
 
+    using HalfOut = typename std::conditional<HALF, PassHalf, NoHalf>::type;
     static constexpr bool want_tip = WANT_TIP;   // compile-time: keeps the accumulation of the
                                                  // pending sample in the same basic block as the
                                                  // arithmetic of the current one
@@ -677,6 +686,7 @@ struct FastSweep {
     double Qw, Qx, Qy, Qz, Px, Py, Pz; // suffix product E_k ... E_tip
     double pux, puy, puz;              // pending sample (not yet accumulated)
     double a_tip, pos;
+    double hs, hc;                     // HALF: sin/cos(al[T-1] / 2)
 
     CTR_HD FastSweep(const KRobot& rb_, const Ctl<L>& c_, const OnSample& os)
         : rb(rb_), c(c_), on_sample(os)
@@ -686,6 +696,8 @@ struct FastSweep {
         for (int t = 0; t < T; ++t) { al[t] = c.al[t]; uzs[t] = 0.0; sn[t] = 0.0; cs[t] = 1.0; }
 #pragma unroll
         for (int t = 1; t < T; ++t) fast_sincos(al[t], sn[t], cs[t]);
+        hs = 0.0; hc = 1.0;
+        if (HALF) fast_sincos(0.5 * al[T - 1], hs, hc);
 #pragma unroll
         for (int t = 0; t + 1 < T; ++t) hko[t] = c.h * rb.onu[t] * rb.kappa[L::sec_of(t)];
         Qw = 1.0; Qx = Qy = Qz = 0.0; Px = Py = Pz = 0.0;
@@ -830,7 +842,25 @@ struct FastSweep {
             // sin/cos of the new angles, for the next sample
 #pragma unroll
             for (int t = 1; t < T; ++t) {
-                if (HOT && ROT) {
+                if (HALF && t == T - 1 && HOT && ROT) {
+                    // half-angle pair rotated by d/2, full-angle pair by the double-angle formulas (3 instead of 12
+                    // instructions for the pair the sweep needs, and no separate sin/cos of the frame's half angle)
+                    const double e  = 0.5 * dl[t];
+                    const double e2 = e * e;
+                    double pc = x_fma(CTRK_FC.qa4[0], e2, CTRK_FC.qa4[1]);
+                    double ps = x_fma(CTRK_FC.qb4[0], e2, CTRK_FC.qb4[1]);
+                    pc = x_fma(pc, e2, CTRK_FC.qa4[2]);
+                    ps = x_fma(ps, e2, CTRK_FC.qb4[2]);
+                    pc = x_fma(pc, e2, CTRK_FC.qa4[3]);
+                    ps = x_fma(ps, e2, CTRK_FC.qb4[3]);
+                    const double cd = x_fma(pc, e2, 1.0);
+                    const double sd = x_fma(e * e2, ps, e);
+                    const double s1 = x_fma(hc, sd, hs * cd);
+                    const double c1 = x_fma(-hs, sd, hc * cd);
+                    hs = s1; hc = c1;
+                    sn[t] = 2.0 * (s1 * c1);
+                    cs[t] = x_fma(c1, c1, -(s1 * s1));
+                } else if (HOT && ROT) {
                     const double d  = dl[t];
                     const double d2 = d * d;
                     double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
@@ -846,12 +876,16 @@ struct FastSweep {
                     sn[t] = s1; cs[t] = c1;
                 } else if (HOT) {
                     sincos_bounded(al[t], sn[t], cs[t]);
+                    if (HALF && t == T - 1) sincos_bounded(0.5 * al[t], hs, hc);
                 } else {
                     fast_sincos(al[t], sn[t], cs[t]);
+                    if (HALF && t == T - 1) fast_sincos(0.5 * al[t], hs, hc);
                 }
             }
+            if (HALF && T == 1) { hs = 0.0; hc = 1.0; }      // tube 0 is pinned to 0 after the head step
         }
         on_sample(k, uxs[T - 1], uy_in, uz_k, a_k);
+        if (HALF) HalfOut::set(on_sample, hs, hc);
         if (want_tip) {
             if (TAIL) {
                 accumulate_generic(uxs[T - 1], uy_in, uz_k);
@@ -1295,29 +1329,43 @@ struct PendingFrameEmitter {
     int           pk;                    // pending sample, -1: none
     double        pux, puy, puz, pal;
     double        psxy, pm;              // |u_xy|^2 and (h|u|/2)^2 of the pending sample (pending_hot)
+    double        phs, phc;              // sin/cos(alpha_k / 2) of the pending sample (FastSweep<.., HALF>)
+    double        ths, thc;              // sin/cos(theta / 2)
 
     CTR_HD void operator()(int k, double ux, double uy, double uz, double al)
     {
         pk = (k <= ktip) ? k : -1;
         pux = ux; puy = uy; puz = uz; pal = al;
     }
-    // branch-free forms apply: series SE(3) step of the first tier, bounded frame angle
+    CTR_HD void set_half(double s, double c) { phs = s; phc = c; }
+    // branch-free forms apply: series SE(3) step of the first tier
     CTR_HD bool pending_hot()
     {
         psxy = x_fma(puy, puy, pux * pux);
         const double n2 = x_fma(puz, puz, psxy);
         pm = n2 * kc.hh2;
-        return pk >= 0 && le_nonneg(kc.ztol2, n2) && hi_word(pm) < 0x3f700000 &&
-               (hi_word(pal + theta) & 0x7fffffff) < 0x40900000;
+        return pk >= 0 && le_nonneg(kc.ztol2, n2) && hi_word(pm) < 0x3f700000;
     }
     CTR_HD void emit_hot()               // after pending_hot() returned true
     {
-        double shf, chf, F[12];
-        sincos_bounded(0.5 * (pal + theta), shf, chf);
+        double F[12];
+        // (alpha_k + theta) / 2 from the carried half-angle pair and the constant pair of theta / 2
+        const double shf = x_fma(phc, ths, phs * thc);
+        const double chf = x_fma(-phs, ths, phc * thc);
         qt_frame(*rb, I, shf, chf, F);
         store(pk, F);
-        double qa, qb, qc;
-        se3_series4(pm, qa, qb, qc);
+        // step series: rotation to full precision; the third-order translation term only needs ~1e-9 relative
+        // (FastSweep::accumulate_hot)
+        double qa = x_fma(CTRK_FC.qa4[0], pm, CTRK_FC.qa4[1]);
+        double qb = x_fma(CTRK_FC.qb4[0], pm, CTRK_FC.qb4[1]);
+        double qc = x_fma(CTRK_FC.qc4[2], pm, CTRK_FC.qc4[3]);
+        qa = x_fma(qa, pm, CTRK_FC.qa4[2]);
+        qb = x_fma(qb, pm, CTRK_FC.qb4[2]);
+        qc = x_fma(qc, pm, 1.0 / 6.0);
+        qa = x_fma(qa, pm, CTRK_FC.qa4[3]);
+        qb = x_fma(qb, pm, CTRK_FC.qb4[3]);
+        qa = x_fma(qa, pm, 1.0);
+        qb = x_fma(qb, pm, 1.0);
         const double b2 = kc.h * qb, b = kc.hh * qb;
         QT E;
         E.w = qa; E.x = b * pux; E.y = b * puy; E.z = b * puz;
@@ -1339,6 +1387,16 @@ struct PendingFrameEmitter {
         I = qt_mul_inv(I, E);
     }
 };
+
+// The emitter of one configuration: I starts as the total product `total` of a first sweep.
+template <class L, class StoreFrame>
+CTR_HD PendingFrameEmitter<StoreFrame> make_frame_emitter(const KRobot& rb, const Ctl<L>& c, const StoreFrame& store, const QT& total)
+{
+    PendingFrameEmitter<StoreFrame> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, store, total, c.nframes - 1,
+                                       -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+    fast_sincos(0.5 * c.theta, em.ths, em.thc);
+    return em;
+}
 
 // ---- finite-difference Jacobians (robot_i.h:901-1072, :41-56) ------------------------------------
 // on_sample functor: the frame product of sample ks, B = E_0 ... E_ks, accumulated next to the solver's own

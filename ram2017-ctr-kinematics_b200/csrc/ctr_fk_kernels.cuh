@@ -85,11 +85,12 @@ __device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg)
 }
 
 // ---- tip-only kernel ---------------------------------------------------------------------------
-// Register budget: 4 CTAs of 128 threads per SM (16 warps) leaves 128 registers per thread.  Measured
-// on B200 (tools/tune_tip.cu): capping registers for 20 or 24 warps/SM is 3-5 % slower — the sweep
-// is bound by FP64 issue, not by latency that more warps could hide.
+// Register budget: 4 CTAs of 128 threads per SM (16 warps) leaves 128 registers per thread; layouts of 4 and more
+// tubes get 3 CTAs and 168 registers (tip_blocks_per_sm, ctr_fk_launch.h).  Measured on B200 (tools/tune_tip.cu):
+// capping registers for 20 or 24 warps/SM is 3-5 % slower — the sweep is bound by FP64 issue, not by latency that
+// more warps could hide.
 template <class L, bool FAST>
-__global__ void __launch_bounds__(kBlock, FAST ? 4 : 1)
+__global__ void __launch_bounds__(kBlock, FAST ? tip_blocks_per_sm(L::T, L::S) : 1)
 fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     int64_t i;
@@ -140,7 +141,7 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
 // peer, 2.3x slower than no collective at all with seven (8 GPUs: 4.80 ms against 2.04 ms); kept for permuted
 // rows and as CTR_FK_FLAG_GATHER_ROWWISE for comparison.
 template <class L>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, tip_blocks_per_sm(L::T, L::S))
 fk_tip_gather_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     __shared__ double2 stage[kBlock * 6];
@@ -351,7 +352,7 @@ struct FrameStoreAos {       // one configuration's frames back to back: 3 full-
 
 // LAYOUT: 0 = SoA [MaxS][12][B], 1 = AoS [B][MaxS][12] with a 32-byte aligned buffer, 2 = AoS, 16-byte aligned
 template <class L, int LAYOUT>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, tip_blocks_per_sm(L::T, L::S))
 fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -375,17 +376,13 @@ fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_cons
     }
     if (LAYOUT == 0) {
         const FrameStoreSoa fs{a.backbone + cfg, a.B, a.tip ? a.tip + cfg * 12 : nullptr, c.nframes - 1};
-        const PendingFrameEmitter<FrameStoreSoa> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
-                                                    -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        FastSweep<L, false, PendingFrameEmitter<FrameStoreSoa>> s2(rb, c, em);
+        FastSweep<L, false, PendingFrameEmitter<FrameStoreSoa>, true> s2(rb, c, make_frame_emitter<L>(rb, c, fs, T));
         s2.run_emit();
         if (a.radius) fill_radius<L>(rb, c, a.radius + cfg, a.B);
     } else {
         using Store = FrameStoreAos<LAYOUT == 1>;
         const Store fs{a.backbone + cfg * 12 * (int64_t)rb.maxs, a.tip ? a.tip + cfg * 12 : nullptr, c.nframes - 1};
-        const PendingFrameEmitter<Store> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
-                                            -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        FastSweep<L, false, PendingFrameEmitter<Store>> s2(rb, c, em);
+        FastSweep<L, false, PendingFrameEmitter<Store>, true> s2(rb, c, make_frame_emitter<L>(rb, c, fs, T));
         s2.run_emit();
         if (a.radius) fill_radius<L>(rb, c, a.radius + cfg * (int64_t)rb.maxs, 1);
     }

@@ -78,6 +78,13 @@ struct ShootArgs {
 };
 
 constexpr int kBlock = 128;     // threads per CTA for every solver kernel
+// Resident CTAs per SM the FAST tip solver is compiled for.  The sweep of a 3-tube robot fits 128 registers (4 CTAs,
+// 16 warps/SM); from 4 tubes (or 3 sections) on the state no longer does and a 128-register build spills and rematerialises.  The
+// kernel's rate does not depend on the warp count between 8 and 16 warps/SM (it is bound by the FP64 pipe, not by
+// latency: tools/tune_tip.cu, 1M configurations, N=256: 3 tubes 2.008 / 1.998 ms at 12 / 16 warps; 4 tubes 2.388 /
+// 2.494; 5 tubes 2.794 / 2.912; 6 tubes 3.289 / 3.463; 3 tubes in 3 sections 2.074 / 2.089 with an 8-byte spill at 128 registers), so
+// those layouts get up to 168 registers and 3 CTAs.
+constexpr int tip_blocks_per_sm(int ntubes, int nsections) { return (ntubes >= 4 || nsections >= 3) ? 3 : 4; }
 constexpr int kBinWindow = 4096;        // step-mode binning sorts windows of this many consecutive configurations
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)

@@ -179,9 +179,7 @@ void emit_full_all(const KRobot& rb, const double* jv, int64_t B, int mode, doub
         QT T;
         T.w = s1.Qw; T.x = s1.Qx; T.y = s1.Qy; T.z = s1.Qz; T.px = s1.Px; T.py = s1.Py; T.pz = s1.Pz;
         FrameStoreHost fs{frames + i * 12 * (int64_t)rb.maxs};
-        PendingFrameEmitter<FrameStoreHost> em{&rb, make_step_consts(c.h, rb.ztol), c.theta, fs, T, c.nframes - 1,
-                                               -1, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        FastSweep<L, false, PendingFrameEmitter<FrameStoreHost>> s2(rb, c, em);
+        FastSweep<L, false, PendingFrameEmitter<FrameStoreHost>, true> s2(rb, c, make_frame_emitter<L>(rb, c, fs, T));
         s2.run_emit();
     }
 }

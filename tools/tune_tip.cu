@@ -31,10 +31,9 @@ tip_variant(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
-template <int BLOCK, int MINB>
+template <class L, int BLOCK, int MINB>
 void run(const KRobot& rb, FkArgs a, const char* tag)
 {
-    using L = Lay<2, 2, 1, 0>;
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, tip_variant<L, BLOCK, MINB>));
     int occ = 0;
@@ -57,47 +56,51 @@ void run(const KRobot& rb, FkArgs a, const char* tag)
            fa.numRegs, fa.localSizeBytes, occ, occ * BLOCK / 32, best, a.B / (best * 1e-3));
 }
 
-int main()
+int main(int argc, char** argv)
 {
+    // robot: 0 = ctr_sec2_tub3 (Lay<2,2,1,0>), 1 = ctr_sec3_tub3 (Lay<3,1,1,1>), 2 = ctr_sec3_tub5 (Lay<3,2,2,1>)
+    const int which = argc > 1 ? atoi(argv[1]) : 0;
     ctr_robot_desc d = {};
-    d.nsections = 2; d.max_samples = 256;
+    d.max_samples = 256;
     d.init_trafo[0] = d.init_trafo[4] = d.init_trafo[8] = 1.0;
-    d.sec[0].ntube = 2; d.sec[0].length = 0.06647;
-    d.sec[0].stiffness[0] = d.sec[0].stiffness[1] = 5; d.sec[0].curvature[0] = d.sec[0].curvature[1] = 52.2;
-    d.sec[0].radius[0] = 0.00125; d.sec[0].radius[1] = 0.001; d.sec[0].poisson[0] = d.sec[0].poisson[1] = 0.3;
-    d.sec[1].ntube = 1; d.sec[1].length = 0.0667; d.sec[1].stiffness[0] = 1; d.sec[1].curvature[0] = 52.63;
-    d.sec[1].radius[0] = 0.001; d.sec[1].poisson[0] = 0.3;
+    auto sec = [&](int s, int nt, double len, double k0, double k1, double kap, double r0) {
+        d.sec[s].ntube = nt; d.sec[s].length = len; d.sec[s].stiffness[0] = k0; d.sec[s].stiffness[1] = k1;
+        d.sec[s].curvature[0] = d.sec[s].curvature[1] = kap; d.sec[s].radius[0] = r0; d.sec[s].radius[1] = r0 * 0.8;
+        d.sec[s].poisson[0] = d.sec[s].poisson[1] = 0.3;
+    };
+    if (which == 0) { d.nsections = 2; sec(0, 2, 0.06647, 5, 5, 52.2, 0.00125); sec(1, 1, 0.0667, 1, 0, 52.63, 0.001); }
+    if (which == 1) { d.nsections = 3; sec(0, 1, 0.06647, 5, 0, 52.2, 0.00125); sec(1, 1, 0.0667, 1, 0, 52.63, 0.001); sec(2, 1, 0.01265, 0.05, 0, 1e-6, 0.0005); }
+    if (which == 2) { d.nsections = 3; sec(0, 2, 0.06647, 5, 5, 52.2, 0.00125); sec(1, 2, 0.0667, 1, 1, 52.63, 0.001); sec(2, 1, 0.01265, 0.05, 0, 1e-6, 0.0005); }
+    if (which == 3) { d.nsections = 3; sec(0, 2, 0.06647, 5, 5, 52.2, 0.00125); sec(1, 1, 0.0667, 1, 0, 52.63, 0.001); sec(2, 1, 0.01265, 0.05, 0, 1e-6, 0.0005); }
+    if (which == 4) { d.nsections = 3; sec(0, 2, 0.06647, 5, 5, 52.2, 0.00125); sec(1, 2, 0.0667, 1, 1, 52.63, 0.001); sec(2, 2, 0.01265, 0.05, 0.05, 1.0, 0.0005); }
     KRobot rb;
     if (make_krobot(&d, &rb)) return 1;
+    const int njv = 1 + d.nsections + (which == 0 ? 3 : which == 1 ? 3 : which == 2 ? 5 : which == 3 ? 4 : 6);
     const int64_t B = 1000000;
-    std::vector<double> jv(B * 6);
+    std::vector<double> jv(B * njv);
     SamplerTable tb; make_sampler_table(&d, &tb);
-    for (int64_t i = 0; i < B; ++i) for (int j = 0; j < 6; ++j) jv[i * 6 + j] = tb.scale[j] * sampler_u01(20171, i, j);
+    // argv[3] = 1: every configuration gets configuration 0's extensions (Phi), so interval bounds coincide across a warp
+    const bool same_phi = argc > 3 && atoi(argv[3]) == 1;
+    for (int64_t i = 0; i < B; ++i) for (int j = 0; j < njv; ++j) jv[i * njv + j] = tb.scale[j] * sampler_u01(20171, i, j);
+    if (same_phi) {
+        int off = 1;
+        for (int s = 0; s < d.nsections; ++s) { for (int64_t i = 1; i < B; ++i) jv[i * njv + off] = jv[off]; off += 1 + d.sec[s].ntube; }
+    }
     FkArgs a = {};
     double *djv, *dtip;
-    CK(cudaMalloc(&djv, sizeof(double) * B * 6)); CK(cudaMalloc(&dtip, sizeof(double) * B * 12));
-    CK(cudaMemcpy(djv, jv.data(), sizeof(double) * B * 6, cudaMemcpyHostToDevice));
-    a.jv = djv; a.B = B; a.mode = 1; a.nsamples = 256; a.tip = dtip;
-    run<128, 4>(rb, a, "base");
-    run<128, 3>(rb, a, "");
-    run<64, 7>(rb, a, "");
-    run<64, 6>(rb, a, "");
-    run<32, 14>(rb, a, "");
-    run<32, 13>(rb, a, "");
-    run<128, 5>(rb, a, "");
-    run<128, 6>(rb, a, "");
-    run<64, 8>(rb, a, "");
-    run<64, 9>(rb, a, "");
-    run<64, 10>(rb, a, "");
-    run<64, 12>(rb, a, "");
-    run<96, 6>(rb, a, "");
-    run<32, 16>(rb, a, "");
-    run<32, 19>(rb, a, "");
-    run<32, 24>(rb, a, "");
-    run<256, 2>(rb, a, "");
-    run<256, 3>(rb, a, "");
+    CK(cudaMalloc(&djv, sizeof(double) * B * njv)); CK(cudaMalloc(&dtip, sizeof(double) * B * 12));
+    CK(cudaMemcpy(djv, jv.data(), sizeof(double) * B * njv, cudaMemcpyHostToDevice));
+    a.jv = djv; a.B = B; a.mode = 1; a.nsamples = argc > 2 ? atoi(argv[2]) : 256; a.tip = dtip;
+#ifndef TUNE_TAG
+#define TUNE_TAG "cur"
+#endif
+    if (which == 0) { run<Lay<2, 2, 1, 0>, 128, 3>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 128, 4>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 128, 5>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 64, 8>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 64, 10>(rb, a, TUNE_TAG); }
+    if (which == 1) { run<Lay<3, 1, 1, 1>, 128, 3>(rb, a, TUNE_TAG); run<Lay<3, 1, 1, 1>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 1, 1, 1>, 128, 5>(rb, a, TUNE_TAG); }
+    if (which == 3) { run<Lay<3, 2, 1, 1>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 2, 1, 1>, 128, 3>(rb, a, TUNE_TAG); }
+    if (which == 4) { run<Lay<3, 2, 2, 2>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 2>, 128, 3>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 2>, 128, 2>(rb, a, TUNE_TAG); }
+    if (which == 2) { run<Lay<3, 2, 2, 1>, 128, 2>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 1>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 1>, 128, 3>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 1>, 128, 5>(rb, a, TUNE_TAG); }
     std::vector<double> tip(12);
-    CK(cudaMemcpy(tip.data(), dtip, 96, cudaMemcpyDeviceToHost));
-    printf("tip[0] translation %.15g %.15g %.15g\n", tip[9], tip[10], tip[11]);
+    CK(cudaMemcpy(tip.data(), dtip + 12 * 4321, 96, cudaMemcpyDeviceToHost));
+    printf("robot %d N %d tip[4321] translation %.15g %.15g %.15g\n", which, a.nsamples, tip[9], tip[10], tip[11]);
     return 0;
 }
