@@ -246,6 +246,9 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
  * configuration whose i_sample is not below its sample count gets NaN in jac_sample/sample (the reference would
  * read a stale frame). */
 #define CTR_FK_FLAG_JAC_GIVEN_POSES 0x100u
+/* flags: CTR_FK_FLAG_JAC_GIVEN_POSES, CTR_FK_FLAG_NO_BINNING, CTR_FK_FLAG_STRICT (every solve in the reference's
+ * operation order: the Jacobian then differs from the reference's own only through libm and the frame product's
+ * association). */
 int ctr_fk_jacobian_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                              int32_t nsamples, int32_t i_sample, double fd_trans, double fd_rot,
                              uint32_t flags, double* jac_tip, double* jac_sample, double* tip,
@@ -270,6 +273,17 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
 /* The same with HOST pointers (synchronous; staged through the device). */
 int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double angle_step,
                           double arc_step, double min_degree, int32_t* stable, double* degree);
+/* Both with flags: CTR_FK_FLAG_STRICT runs every sweep of the scan in the reference's operation order.  The verdict
+ * is the SIGN of a base-angle difference between two scan points (robot_i.h:805, :873); FAST arithmetic moves that
+ * difference by ~1e-13 rad, so a configuration whose smallest difference lies that close to zero can flip — STRICT
+ * exists for callers who need the reference's verdict there too.
+ * angle_step must advance a scan at 2 pi (2 pi + angle_step > 2 pi), else CTR_FK_E_ARG. */
+int ctr_fk_stability_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, double angle_step,
+                              double arc_step, double min_degree, uint32_t flags, int32_t* stable,
+                              double* degree, void* stream);
+int ctr_fk_stability_host_ex(ctr_fk_handle h, const double* jv, int64_t B, double angle_step,
+                             double arc_step, double min_degree, uint32_t flags, int32_t* stable,
+                             double* degree);
 
 /* Base-angle-actuated forward kinematics (not in the reference): the alpha
  * slots of `jv_base` hold the tube angles AT THE BASE (what the actuators set) instead of at the

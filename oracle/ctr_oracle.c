@@ -615,3 +615,49 @@ int ctr_oracle_degree_stability(const ctr_robot_desc* desc, const double* jv, do
     scratch_free(&w);
     return 0;
 }
+
+static int ctr_fk_desc_njoints_local(const ctr_robot_desc* d)
+{
+    int t = 0;
+    for (int s = 0; s < d->nsections; ++s) t += d->sec[s].ntube;
+    return 1 + d->nsections + t;
+}
+
+/* ---- batch forms of the callers (OpenMP over configurations; each call builds its own model and scratch) --------- */
+int ctr_oracle_jacobian_batch(const ctr_robot_desc* desc, const double* jv, int64_t B, int mode, double step,
+                              int32_t nsamples, int32_t i_sample, double fd_trans, double fd_rot, int nthreads,
+                              double* jac_tip, double* jac_sample, double* tip, int32_t* n_out, int32_t* rc_out)
+{
+    if (!desc || !jv || !jac_tip || !rc_out) return CTR_FK_E_NULL;
+    const int njv = ctr_fk_desc_njoints_local(desc);
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t i = 0; i < B; ++i) {
+        double t12[12], s12[12];
+        int32_t n = 0;
+        rc_out[i] = ctr_oracle_jacobian_ex(desc, jv + i * njv, mode, step, nsamples, i_sample, fd_trans, fd_rot,
+                                           jac_tip + i * 6 * njv, jac_sample ? jac_sample + i * 6 * njv : NULL, t12, s12, &n);
+        if (tip) memcpy(tip + 12 * i, t12, sizeof t12);
+        if (n_out) n_out[i] = n;
+    }
+    return 0;
+}
+
+/* stable[i]: 1 / 0, < 0 = error code of that configuration; degree[i] as calcDegreeStability. */
+int ctr_oracle_stability_batch(const ctr_robot_desc* desc, const double* jv, int64_t B, double angle_step,
+                               double arc_step, double min_degree, int nthreads, int32_t* stable, double* degree)
+{
+    if (!desc || !jv || !stable || !degree) return CTR_FK_E_NULL;
+    const int njv = ctr_fk_desc_njoints_local(desc);
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t i = 0; i < B; ++i) {
+        int st = 0;
+        double dg = 0.0;
+        const int rc = ctr_oracle_degree_stability(desc, jv + i * njv, angle_step, arc_step, min_degree, &dg, &st);
+        stable[i] = rc ? (rc < 0 ? rc : -rc) : st;
+        degree[i] = rc ? NAN : dg;
+    }
+    return 0;
+}
+

@@ -64,6 +64,14 @@ int ctr_oracle_stability(const ctr_robot_desc* desc, const double* jv, double an
 int ctr_oracle_degree_stability(const ctr_robot_desc* desc, const double* jv, double angle_step,
                                 double arc_step, double min_degree, double* degree, int* stable_out);
 
+/* Batch forms (OpenMP over configurations).  rc_out[i] = return code of configuration i (Jacobian); stable[i] < 0 =
+ * error code (stability). */
+int ctr_oracle_jacobian_batch(const ctr_robot_desc* desc, const double* jv, int64_t B, int mode, double step,
+                              int32_t nsamples, int32_t i_sample, double fd_trans, double fd_rot, int nthreads,
+                              double* jac_tip, double* jac_sample, double* tip, int32_t* n_out, int32_t* rc_out);
+int ctr_oracle_stability_batch(const ctr_robot_desc* desc, const double* jv, int64_t B, double angle_step,
+                               double arc_step, double min_degree, int nthreads, int32_t* stable, double* degree);
+
 int ctr_oracle_max_threads(void);
 
 #ifdef __cplusplus

@@ -37,6 +37,11 @@ def load():
         lib.ctr_oracle_degree_stability.restype = C.c_int
         lib.ctr_oracle_degree_stability.argtypes = [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P]
         lib.ctr_oracle_max_threads.restype = C.c_int
+        lib.ctr_oracle_jacobian_batch.restype = C.c_int
+        lib.ctr_oracle_jacobian_batch.argtypes = [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_int32, C.c_double,
+                                                  C.c_double, C.c_int, _P, _P, _P, _P, _P]
+        lib.ctr_oracle_stability_batch.restype = C.c_int
+        lib.ctr_oracle_stability_batch.argtypes = [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, _P, _P]
         _lib = lib
     return _lib
 
@@ -122,3 +127,30 @@ def degree_stability(desc, jv, angle_step, arc_step, min_degree=-1.0):
     if rc != 0:
         raise RuntimeError("oracle degree_stability error %d" % rc)
     return deg.value, st.value
+
+
+def jacobian_batch(desc, jv, mode, step=0.0, nsamples=0, i_sample=-1, fd_trans=1e-5, fd_rot=1e-4, nthreads=None):
+    """calcJacobian over B configurations (OpenMP); returns dict(jac [B][njv][6], jac_sample, tip, n, rc)."""
+    jv = np.ascontiguousarray(jv, dtype=np.float64)
+    B, njv = jv.shape
+    jac = np.zeros((B, njv, 6)); js = np.zeros((B, njv, 6)) if i_sample >= 0 else None
+    tip = np.zeros((B, 12)); n = np.zeros(B, np.int32); rc = np.zeros(B, np.int32)
+    r = load().ctr_oracle_jacobian_batch(C.addressof(desc), jv.ctypes.data, B, mode, step, nsamples, i_sample,
+                                         fd_trans, fd_rot, nthreads or max_threads(), jac.ctypes.data,
+                                         js.ctypes.data if js is not None else None, tip.ctypes.data, n.ctypes.data, rc.ctypes.data)
+    if r != 0:
+        raise RuntimeError("oracle jacobian_batch error %d" % r)
+    return dict(jac=jac, jac_sample=js, tip=tip, n=n, rc=rc)
+
+
+def stability_batch(desc, jv, angle_step, arc_step, min_degree=-1.0, nthreads=None):
+    """calcDegreeStability over B configurations (OpenMP); returns (stable [B] int32 (< 0: error), degree [B])."""
+    jv = np.ascontiguousarray(jv, dtype=np.float64)
+    B = jv.shape[0]
+    st = np.zeros(B, np.int32); dg = np.zeros(B)
+    r = load().ctr_oracle_stability_batch(C.addressof(desc), jv.ctypes.data, B, angle_step, arc_step,
+                                          min_degree, nthreads or max_threads(), st.ctypes.data, dg.ctypes.data)
+    if r != 0:
+        raise RuntimeError("oracle stability_batch error %d" % r)
+    return st, dg
+

@@ -698,7 +698,8 @@ int ctr_fk_jacobian_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, int m
         if (eo != cudaSuccess) return cuda_fail("step-mode binning", eo);
         a.order = order;
     }
-    cudaError_t e = launch_jacobian(h->key, h->rb, a, (cudaStream_t)stream);
+    cudaError_t e = (flags & CTR_FK_FLAG_STRICT) ? launch_jacobian_strict(h->key, h->rb, a, (cudaStream_t)stream)
+                                                 : launch_jacobian(h->key, h->rb, a, (cudaStream_t)stream);
     if (order) cudaFreeAsync(order, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail("jacobian kernel launch", e);
     return 0;
@@ -773,16 +774,33 @@ int ctr_fk_jacobian_host(ctr_fk_handle h, const double* jv, int64_t B, int32_t n
                                    nullptr, nullptr);
 }
 
+namespace {
+// The scan `scan += angle_step; scan <= end` (robot_i.h:793, :861) must advance everywhere on [0, 2 pi]: a step that
+// is absorbed by rounding would scan forever (the reference hangs; a persistent kernel would hang the GPU).
+int check_angle_step(double angle_step, double min_degree)
+{
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    if (!(angle_step > 0.0) || !std::isfinite(angle_step) || !std::isfinite(min_degree) || !(two_pi + angle_step > two_pi)) {
+        set_error("angle step must be finite, > 0 and large enough to advance a scan at 2 pi (> 4.5e-16); min_degree finite");
+        return CTR_FK_E_ARG;
+    }
+    return 0;
+}
+}  // namespace
+
 int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,
                            double min_degree, int32_t* stable, double* degree, void* stream)
+{
+    return ctr_fk_stability_batch_ex(h, jv, B, angle_step, arc_step, min_degree, 0, stable, degree, stream);
+}
+
+int ctr_fk_stability_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,
+                              double min_degree, uint32_t flags, int32_t* stable, double* degree, void* stream)
 {
     int rc = check_common(h, jv, B, CTR_FK_MODE_STEP, arc_step, 0);
     if (rc) return rc;
     if ((rc = check_align(h, jv, nullptr, nullptr))) return rc;
-    if (!(angle_step > 0.0) || !std::isfinite(angle_step) || !std::isfinite(min_degree)) {
-        set_error("angle step must be finite and > 0, min_degree finite");
-        return CTR_FK_E_ARG;
-    }
+    if ((rc = check_angle_step(angle_step, min_degree))) return rc;
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
@@ -795,7 +813,8 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
     if (e != cudaSuccess) return cuda_fail("ticket allocation", e);
     e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     a.ticket = ticket;
-    if (e == cudaSuccess) e = launch_stability(h->key, h->rb, a, h->sm_count, st);
+    if (e == cudaSuccess) e = (flags & CTR_FK_FLAG_STRICT) ? launch_stability_strict(h->key, h->rb, a, h->sm_count, st)
+                                                           : launch_stability(h->key, h->rb, a, h->sm_count, st);
     cudaFreeAsync(ticket, st);
     if (e != cudaSuccess) return cuda_fail("stability kernel launch", e);
     return 0;
@@ -804,8 +823,15 @@ int ctr_fk_stability_batch(ctr_fk_handle h, const double* jv, int64_t B, double 
 int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,
                           double min_degree, int32_t* stable, double* degree)
 {
+    return ctr_fk_stability_host_ex(h, jv, B, angle_step, arc_step, min_degree, 0, stable, degree);
+}
+
+int ctr_fk_stability_host_ex(ctr_fk_handle h, const double* jv, int64_t B, double angle_step, double arc_step,
+                             double min_degree, uint32_t flags, int32_t* stable, double* degree)
+{
     int rc = check_common(h, jv, B, CTR_FK_MODE_STEP, arc_step, 0);
     if (rc) return rc;
+    if ((rc = check_angle_step(angle_step, min_degree))) return rc;
     if (B == 0) return 0;
     DeviceGuard g(h->device);
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
@@ -821,7 +847,7 @@ int ctr_fk_stability_host(ctr_fk_handle h, const double* jv, int64_t B, double a
     int32_t* d_st = (int32_t*)(d + b_jv + b_deg);
     e = cudaMemcpyAsync(d_jv, jv, n_jv, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        rc = ctr_fk_stability_batch(h, d_jv, B, angle_step, arc_step, min_degree, d_st, d_deg, st);
+        rc = ctr_fk_stability_batch_ex(h, d_jv, B, angle_step, arc_step, min_degree, flags, d_st, d_deg, st);
         if (rc == 0) {
             if (stable) e = cudaMemcpyAsync(stable, d_st, b_st, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess && degree) e = cudaMemcpyAsync(degree, d_deg, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st);

@@ -1443,21 +1443,47 @@ CTR_HD void jac_column0(const KRobot& rb, const double* f, double* jac)
     jac[3] = zx; jac[4] = zy; jac[5] = zz;
 }
 
+// STRICT counterpart: the 3x4 product in the reference's operation order (robot_i.h:705-717)
+struct SampleProductStrict {
+    double  h, ztol;
+    int     ks;
+    double* M;        // [12], starts as the identity
+    double* a_s;
+    CTR_HD void operator()(int k, double ux, double uy, double uz, double al) const
+    {
+        if (k > ks) return;
+        if (k == ks) *a_s = al;
+        double e[12];
+        tf_step_strict(ux, uy, uz, h, ztol, e);
+        tf_mul(e, M, M);
+    }
+};
+
 // One solve that yields the tip frame and, when ks >= 0, the frame of sample ks.
-template <class L, bool WITH_SAMPLE>
+template <class L, bool WITH_SAMPLE, bool FAST = true>
 CTR_HD void solve_tip_and_sample(const KRobot& rb, const Ctl<L>& c, int ks, double* tip, double* smp)
 {
     if (!WITH_SAMPLE || ks < 0) {
-        solve_fast<L, true>(rb, c, tip, nullptr, NoSample{});
+        if (FAST) solve_fast<L, true>(rb, c, tip, nullptr, NoSample{});
+        else      solve_strict<L, true>(rb, c, tip, nullptr, NoSample{});
         return;
     }
-    QT     B  = qt_identity();
     double as = 0.0;
-    SampleProduct f{make_step_consts(c.h, rb.ztol), ks, &B, &as};
-    solve_fast<L, true>(rb, c, tip, nullptr, f);
-    double sh, ch;
-    fast_sincos(0.5 * (as + c.theta), sh, ch);
-    qt_frame(rb, B, sh, ch, smp);
+    if (FAST) {
+        QT B = qt_identity();
+        SampleProduct f{make_step_consts(c.h, rb.ztol), ks, &B, &as};
+        solve_fast<L, true>(rb, c, tip, nullptr, f);
+        double sh, ch;
+        fast_sincos(0.5 * (as + c.theta), sh, ch);
+        qt_frame(rb, B, sh, ch, smp);
+    } else {
+        double M[12];
+        tf_set_identity(M);
+        SampleProductStrict f{c.h, rb.ztol, ks, M, &as};
+        solve_strict<L, true>(rb, c, tip, nullptr, f);
+        const double a = as + c.theta;
+        tf_finish(rb.ini, M, sin(a), cos(a), smp);
+    }
 }
 
 // Every calcJacobian form of the reference for one configuration (what one GPU thread runs):
@@ -1473,7 +1499,8 @@ CTR_HD void solve_tip_and_sample(const KRobot& rb, const Ctl<L>& c, int ks, doub
 // (non-zero: everything NaN), n_out = m_Samples of the base solve.  ks >= m_Samples: the reference would read a
 // stale frame; the sample Jacobian and frame are NaN.
 // WITH_SAMPLE = false compiles the sample-frame path out (tip-only forms keep their register budget).
-template <class L, bool WITH_SAMPLE>
+// FAST = false: every solve is the STRICT solver (CTR_FK_FLAG_STRICT; built with -fmad=false).
+template <class L, bool WITH_SAMPLE, bool FAST = true>
 CTR_HD int jacobian_config(const KRobot& rb, const double* q, int mode, double step, int nsamples, int ks,
                            double fd_trans, double fd_rot, double* jac_tip, double* jac_smp, double* tip_out,
                            double* smp_out, int32_t* n_out, bool given = false)
@@ -1498,7 +1525,7 @@ CTR_HD int jacobian_config(const KRobot& rb, const double* q, int mode, double s
     if (given) {
         for (int e = 0; e < 12; ++e) { tip0[e] = tip_out[e]; smp0[e] = (WITH_SAMPLE && smp_ok) ? smp_out[e] : qnan; }
     } else {
-        solve_tip_and_sample<L, WITH_SAMPLE>(rb, c, kse, tip0, smp0);
+        solve_tip_and_sample<L, WITH_SAMPLE, FAST>(rb, c, kse, tip0, smp0);
         if (tip_out) for (int e = 0; e < 12; ++e) tip_out[e] = tip0[e];
         if (smp_out) for (int e = 0; e < 12; ++e) smp_out[e] = smp_ok ? smp0[e] : qnan;
     }
@@ -1535,7 +1562,7 @@ CTR_HD int jacobian_config(const KRobot& rb, const double* q, int mode, double s
             for (int e = 0; e < 6; ++e) col[e] = cols[e] = qnan;
         } else {
             double tp[12], sp[12];
-            solve_tip_and_sample<L, WITH_SAMPLE>(rb, cp, (kse >= 0 && kse < cp.nframes) ? kse : -1, tp, sp);
+            solve_tip_and_sample<L, WITH_SAMPLE, FAST>(rb, cp, (kse >= 0 && kse < cp.nframes) ? kse : -1, tp, sp);
             jac_column(tip0, tp, dq, col);
             if (WITH_SAMPLE && kse >= 0 && kse < cp.nframes) jac_column(smp0, sp, dq, cols);
             else

@@ -1,7 +1,6 @@
 // ctr_fk_kernels_strict.cu — instantiates the solver kernels with STRICT arithmetic (reference operation order); build this file with -fmad=false
 // for all 14 section layouts.
-#include "ctr_fk_kernels.cuh"
-#include "ctr_fk_internal.h"
+#include "ctr_fk_kernels_extra.cuh"
 
 namespace ctrk {
 
@@ -33,6 +32,13 @@ cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, c
     }
     count_launch();
     return cudaGetLastError();
+}
+
+// CTR_FK_FLAG_STRICT forms of the Jacobian and stability calls: every solve inside them is the STRICT solver
+cudaError_t launch_jacobian_strict(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st) { return launch_jacobian_t<false>(key, rb, a, st); }
+cudaError_t launch_stability_strict(int key, const KRobot& rb, const StabArgs& a, int sm_count, cudaStream_t st)
+{
+    return launch_stability_t<false>(key, rb, a, sm_count, st);
 }
 
 }  // namespace ctrk

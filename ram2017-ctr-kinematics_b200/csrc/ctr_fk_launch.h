@@ -99,6 +99,8 @@ cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, c
 cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);
 // calcStability / calcDegreeStability scan (fast arithmetic, sweep only)
 cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, int sm_count, cudaStream_t st);
+cudaError_t launch_jacobian_strict(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);
+cudaError_t launch_stability_strict(int key, const KRobot& rb, const StabArgs& a, int sm_count, cudaStream_t st);
 // base-angle shooting solve: persistent kernel with a ticket queue (grid sized to the device)
 cudaError_t launch_shoot(int key, const KRobot& rb, const ShootArgs& a, int sm_count, cudaStream_t st);
 

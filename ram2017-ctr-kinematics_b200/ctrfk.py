@@ -88,6 +88,8 @@ SYMBOLS = {
                                           C.c_uint32, _P, _P, _P, _P, _P]),
     "ctr_fk_stability_batch": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "ctr_fk_stability_host": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P]),
+    "ctr_fk_stability_batch_ex": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_uint32, _P, _P, _P]),
+    "ctr_fk_stability_host_ex": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_uint32, _P, _P]),
     "ctr_fk_batch_base": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_double, C.c_int32,
                                     _P, _P, _P, _P, _P]),
     "ctr_fk_sample_joints": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
@@ -298,14 +300,14 @@ class Engine:
                                                _ptr(sample), _ptr(n_out), stream))
 
     def jacobian_host_ex(self, jv, B, mode, fd_trans, fd_rot, jac, step=0.0, nsamples=0, i_sample=-1, jac_sample=None,
-                         tip=None, sample=None, n_out=None, given=False):
+                         tip=None, sample=None, n_out=None, given=False, flags=0):
         _check(load().ctr_fk_jacobian_host_ex(self.handle, _ptr(jv), B, mode, step, nsamples, i_sample, fd_trans, fd_rot,
-                                              FLAG_JAC_GIVEN_POSES if given else 0, _ptr(jac), _ptr(jac_sample), _ptr(tip),
+                                              flags | (FLAG_JAC_GIVEN_POSES if given else 0), _ptr(jac), _ptr(jac_sample), _ptr(tip),
                                               _ptr(sample), _ptr(n_out)))
 
-    def stability(self, jv, B, angle_step, arc_step, min_degree=-1.0, stable=None, degree=None, stream=None):
-        _check(load().ctr_fk_stability_batch(self.handle, _ptr(jv), B, angle_step, arc_step, min_degree,
-                                             _ptr(stable), _ptr(degree), stream))
+    def stability(self, jv, B, angle_step, arc_step, min_degree=-1.0, stable=None, degree=None, stream=None, flags=0):
+        _check(load().ctr_fk_stability_batch_ex(self.handle, _ptr(jv), B, angle_step, arc_step, min_degree, flags,
+                                                _ptr(stable), _ptr(degree), stream))
 
     def batch_base(self, jv_base, B, mode, step=0.0, nsamples=0, tol=1e-11, max_iter=24, jv_tip=None, tip=None,
                    iters=None, status=None, stream=None):

@@ -137,6 +137,34 @@ def test_sampler_matches_numpy_replica_and_distribution(ctrfk, robots):
     assert (jv[:, 0] < 2 * np.pi).all() and (jv[:, 1] < 0.06647).all()
 
 
+def test_sampler_pow_accuracy(ctrfk, robots):
+    """The gamma policy's own pow (ctr_sampler.h::sampler_pow — the same bits on host and device): phi = Length * u^g
+    within 0.75 ulp of the power (+ 0.5 ulp of the product) of the exact value, over eight exponents and eighteen decades
+    of u.  Checked through the host sampler with the numpy replica of its uniform variates."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    d = robots["ctr_sec2_tub3.xml"]
+    B, seed = 1500, 77
+    with np.errstate(over="ignore"):
+        i = np.arange(B, dtype=np.uint64)[:, None]
+        j = np.arange(d.njoints, dtype=np.uint64)[None, :]
+        u = (splitmix64(splitmix64(np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * i) + j) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    worst = 0.0
+    for g in (0.01, 0.3, 0.5, 1.0, 1.7, 2.2, 5.0, 30.0):
+        jv = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_GAMMA, p0=g, lut_size=0)
+        for col, L in ((1, d.sec[0].length), (4, d.sec[1].length)):
+            for k in range(0, B, 3):
+                exact = mp.mpf(L) * mp.power(mp.mpf(float(u[k, col])), mp.mpf(g))
+                if exact < mp.mpf("1e-300"):
+                    continue
+                err = abs(mp.mpf(float(jv[k, col])) - exact) / mp.mpf(float(np.spacing(float(exact))))
+                worst = max(worst, float(err))
+    assert worst < 1.5, worst
+    # special values: u = 0 is never drawn but must not trap; g = 1 is the identity up to the one rounding of L * u
+    jv1 = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_GAMMA, p0=1.0, lut_size=0)
+    assert np.abs(jv1[:, 1] - d.sec[0].length * u[:, 1]).max() <= np.spacing(d.sec[0].length)
+
+
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
 def test_count_samples_matches_oracle(ctrfk, oracle, robots, name):
     d = ctrfk.RobotDesc.from_buffer_copy(robots[name])

@@ -252,7 +252,11 @@ def test_scale_policies_against_the_reference_classes(ctrfk, robots, refs):
     for lut in (0, 16, 64, 256, 1024):
         got = ctrfk.sample_joints_host(d, seed, 0, B, policy=ctrfk.SCALE_GAMMA, p0=2.5, lut_size=lut)
         want = lens * ref_lib.gamma_scale(lut, 2.5, u[:, phi])          # section_i.h:341: m_Length * scaleTrans(u)
-        assert np.array_equal(got[:, phi], want), lut
+        # the reference calls std::pow; the sampler its own pow (the same bits on host and device, < 1 ulp from the
+        # correctly rounded value, ctr_sampler.h) — the two differ by at most 1 ulp of the power: 2 ulp of the product,
+        # 4 ulp after the table's interpolation between two such powers (measured: 2 and 3)
+        assert (np.abs(got[:, phi] - want) <= (2.0 if lut == 0 else 4.0) * np.spacing(np.abs(want))).all(), lut
+        assert (got[:, phi] == want).mean() > 0.85, lut
     # ProportionalScale carries its goal from one configuration to the next (the last-section draw, :286-288);
     # the first goal comes from std::rand() in the reference and from an extra sampler slot here, so configuration 0
     # is compared after handing the reference's first goal to the formula, every later one directly
