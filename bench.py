@@ -55,8 +55,11 @@ def parse():
     ap.add_argument("--soa", action="store_true", help="with --backbone: [MaxS][12][B] output layout (CTR_FK_FLAG_SOA)")
     ap.add_argument("--f32", action="store_true", help="FP32 state arithmetic variant")
     ap.add_argument("--shoot", action="store_true", help="base-angle shooting solve (ctr_fk_batch_base) instead of FK")
-    ap.add_argument("--shoot-max-iter", type=int, default=24,
-                    help="Newton iteration cap of --shoot (99.9 %% of the converging configurations need <= 18)")
+    ap.add_argument("--shoot-max-iter", type=int, default=100,
+                    help="sweep cap of --shoot (naive start with restarts: 99+ %% solved within 100 sweeps, mean 6-11)")
+    ap.add_argument("--shoot-guess", type=float, default=None, metavar="RAD",
+                    help="--shoot with a warm start: the guess is the true tip angles + uniform noise of this amplitude")
+    ap.add_argument("--shoot-rk4", action="store_true", help="--shoot on the continuum model integrated by RK4 (CTR_FK_FLAG_RK4)")
     ap.add_argument("--allgather", action="store_true", help="time an NCCL all-gather of the tip poses too")
     ap.add_argument("--gather-rowwise", action="store_true", help="--allgather-fused with one thread storing its own row (comparison)")
     ap.add_argument("--gather-replicate", type=int, default=1,
@@ -82,7 +85,7 @@ def workload_of(a, **over):
     """The workload a set of command-line arguments (or a `configs` entry) describes."""
     w = types.SimpleNamespace(
         robot=a.robot, batch=a.batch, mode=a.mode, nsamples=a.nsamples, max_samples=a.max_samples, strict=a.strict,
-        backbone=a.backbone, soa=a.soa, f32=a.f32, shoot=a.shoot, shoot_max_iter=a.shoot_max_iter,
+        backbone=a.backbone, soa=a.soa, f32=a.f32, shoot=a.shoot, shoot_max_iter=a.shoot_max_iter, shoot_guess=a.shoot_guess, shoot_rk4=a.shoot_rk4,
         collective=("nccl" if a.allgather else (a.allgather_fused or "none")),
         gather_rowwise=a.gather_rowwise, gather_replicate=a.gather_replicate, nset=2)
     for k, v in over.items():
@@ -471,14 +474,21 @@ def run_workload(ctx, w, steps, warmup, keep=False):
             jb = jvs[s].clone()
             for t in range(1, desc.ntubes):
                 jb[:, idx[t]] = ab[:, t]
+            guess = None
+            if w.shoot_guess is not None:
+                guess = jvs[s].clone()
+                g = torch.Generator(device="cuda"); g.manual_seed(1234 + s)
+                for t in range(1, desc.ntubes):
+                    guess[:, idx[t]] += (torch.rand(B, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * w.shoot_guess
             shoot.append(dict(jvb=jb, jt=torch.empty_like(jb), it=torch.empty(B, dtype=torch.int32, device="cuda"),
-                              st=torch.empty(B, dtype=torch.int32, device="cuda")))
+                              st=torch.empty(B, dtype=torch.int32, device="cuda"), guess=guess))
 
     def one_step(i):
         s = i % NSET
         if w.shoot:
             eng.batch_base(shoot[s]["jvb"], B, mode, step=step_len, nsamples=w.nsamples, tol=1e-11, max_iter=w.shoot_max_iter,
-                           jv_tip=shoot[s]["jt"], tip=tips[s], iters=shoot[s]["it"], status=shoot[s]["st"], stream=stream)
+                           jv_tip=shoot[s]["jt"], tip=tips[s], iters=shoot[s]["it"], status=shoot[s]["st"], stream=stream,
+                           jv_guess=shoot[s]["guess"], flags=ctrfk.FLAG_RK4 if w.shoot_rk4 else 0)
         elif w.f32:
             eng.batch_f32(jvs[s], B, mode, step=step_len, nsamples=w.nsamples, flags=flags, tip=tips[s], stream=stream)
         elif fused is not None:
@@ -582,9 +592,13 @@ def run_workload(ctx, w, steps, warmup, keep=False):
            "dtype": "f32" if w.f32 else "f64", "config": cfg, "arm": {"arithmetic": "strict" if w.strict else "fast"},
            "roofline": roofline, "clocks": clk, "gpu_launches": launches}
     if w.shoot:
+        import numpy as np
         it = shoot[0]["it"].cpu().numpy(); stt = shoot[0]["st"].cpu().numpy()
-        res["shoot"] = {"converged_frac": float((stt == 0).mean()), "mean_iters": float(it[stt == 0].mean()),
-                        "max_iters": int(it.max()), "sweeps_per_config": float(it.mean() + 1)}
+        res["shoot"] = {"converged_frac": float((stt == 0).mean()), "mean_sweeps_converged": float(it[stt == 0].mean()),
+                        "max_sweeps": int(it.max()), "sweeps_per_config": float(it.mean()), "sweep_cap": w.shoot_max_iter,
+                        "start": "x = beta, restarts" if w.shoot_guess is None else "guess within %g rad of the root" % w.shoot_guess,
+                        "integrator": "rk4 (continuum model)" if w.shoot_rk4 else "reference sweep",
+                        "statuses": {int(k): int(v) for k, v in zip(*np.unique(stt, return_counts=True))}}
         cfg["workload"] += " [base-angle shooting solve, not the headline FK]"
     if keep:
         res["_live"] = dict(eng=eng, desc=desc, jvs=jvs, tips=tips, mode=mode, step_len=step_len, flags=flags, seed=seed)
@@ -720,7 +734,7 @@ def run_e2e(ctx, a, w, live):
 
 def extra_workloads(a, world):
     """BASELINE.json configs[2..4] (per-GPU shard sizes of the 8-GPU statement; the same per-GPU work at every N)."""
-    base = dict(mode="F", nsamples=256, max_samples=256, strict=False, soa=False, shoot=False, gather_rowwise=False,
+    base = dict(mode="F", nsamples=256, max_samples=256, strict=False, soa=False, shoot=False, shoot_max_iter=100, shoot_guess=None, shoot_rk4=False, gather_rowwise=False,
                 gather_replicate=1, backbone=False, f32=False, collective="none", nset=2)
     out = []
     c3 = dict(base, robot="ctr_sec3_tub3.xml", batch=2_000_000)

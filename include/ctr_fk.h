@@ -287,27 +287,49 @@ int ctr_fk_stability_host_ex(ctr_fk_handle h, const double* jv, int64_t B, doubl
 
 /* Base-angle-actuated forward kinematics (not in the reference): the alpha
  * slots of `jv_base` hold the tube angles AT THE BASE (what the actuators set) instead of at the
- * tip.  A Newton shooting solve finds the tip angles whose reference sweep ends at those base
- * angles (Jacobian from the tangent-linear sweep), then the ordinary solve produces the pose.
- * Iteration counts differ per configuration; the kernel is persistent and every lane draws its
- * next configuration from a global ticket counter as soon as it converges.
+ * tip.  A damped Newton shooting solve finds the tip angles whose sweep ends at those base angles (Jacobian from the
+ * tangent-linear sweep — the variational equations of the discrete recurrence; backtracking line search on the
+ * residual max-norm; step limiter 1 rad), then the ordinary solve produces the pose.
+ * Sweep counts differ per configuration; the kernel is persistent and every lane draws its
+ * next configuration from a global ticket counter as soon as it finishes (a work queue that absorbs the divergence).
  *   jv_tip [B][n_jv]  out, REQUIRED: jv_base with the alpha slots replaced by the tip angles found
- *                     (feeding it to ctr_fk_batch reproduces `tip`); tube 0's angle passes through
+ *                     (feeding it to ctr_fk_batch reproduces `tip`); tube 0's angle passes through.  On a status other
+ *                     than OK it holds the best estimate reached (lowest residual accepted)
  *   tip    [B][12]    out, nullable
- *   iters  [B]        out, nullable: Newton updates applied
+ *   iters  [B]        out, nullable: sweeps run
  *   status [B]        out, nullable: 0 converged (max |base - wanted| <= tol), 1 Phi out of range,
- *                     2 singular Jacobian (bifurcation point), 3 max_iter reached
- * max_iter: on the shipped robots 99 % of the converging configurations need <= 11 Newton updates and 99.9 %
- * <= 18; 3.7 % of random inputs never converge (these robots are unstable there) and a lane holding one runs
- * alone to the cap, which sets the tail of the persistent kernel — 24 is a good cap, 60 buys 0.08 % more roots.
+ *                     2 singular Jacobian (bifurcation point), 3 max_iter sweeps spent, 4 stalled: the line search
+ *                     could not lower the residual (a fold of the base-angle map — no root on this branch)
+ * These robots are unstable for a large share of random inputs (calcStability) and the base-angle map then has
+ * several roots.  Without a guess the solve starts from x = beta and, when a start stalls, starts again from
+ * reproducible pseudo-random angles until a root is found or max_iter sweeps are spent (so statuses 2 and 4 only come
+ * back together with a guess): on the shipped robots 99.3-100 % of random inputs with a root are solved within 100
+ * sweeps at a mean of 6-11 (a cap of 100 is a good default; the work queue absorbs the tail) — but WHICH root comes
+ * back is arbitrary.  A robot driven at the base follows a branch: pass the previous configuration's solution as the
+ * guess (ctr_fk_batch_base_ex); the solve then never leaves that branch and reports STALLED where it ends.
  * DEVICE pointers. */
 #define CTR_FK_SHOOT_OK        0
 #define CTR_FK_SHOOT_PHI_RANGE 1
 #define CTR_FK_SHOOT_SINGULAR  2
 #define CTR_FK_SHOOT_MAX_ITER  3
+#define CTR_FK_SHOOT_STALLED   4
 int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mode, double step,
                       int32_t nsamples, double tol, int32_t max_iter, double* jv_tip, double* tip,
                       int32_t* iters, int32_t* status, void* stream);
+/* The same with
+ *   jv_guess [B][n_jv]  in, nullable: the alpha slots hold the starting tip angles (warm start / branch tracking);
+ *                       NULL starts from x = beta
+ *   resid    [B]        out, nullable: max |base - wanted| at the returned tip angles
+ *   flags               CTR_FK_FLAG_RK4: shoot on the CONTINUUM rod model integrated tip -> base by
+ *                       classical fixed-step RK4 with the variational equations carried through every stage, instead
+ *                       of on the reference's first-order sweep.  A different discretisation: its roots differ from
+ *                       the reference sweep's by O(h) (halving with h); `tip` is still the reference FK at the tip
+ *                       angles found.  Checked against oracle/ctr_shoot_rk4_py.py, not against the reference. */
+#define CTR_FK_FLAG_RK4 0x1000u
+int ctr_fk_batch_base_ex(ctr_fk_handle h, const double* jv_base, const double* jv_guess, int64_t B, int mode,
+                         double step, int32_t nsamples, double tol, int32_t max_iter, uint32_t flags,
+                         double* jv_tip, double* tip, int32_t* iters, int32_t* status, double* resid,
+                         void* stream);
 
 /* ---- inputs ---------------------------------------------------------------------------- */
 

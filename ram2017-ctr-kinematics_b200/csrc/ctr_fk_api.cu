@@ -865,9 +865,19 @@ int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mod
                       double tol, int32_t max_iter, double* jv_tip, double* tip, int32_t* iters, int32_t* status,
                       void* stream)
 {
+    return ctr_fk_batch_base_ex(h, jv_base, nullptr, B, mode, step, nsamples, tol, max_iter, 0, jv_tip, tip, iters, status,
+                                nullptr, stream);
+}
+
+int ctr_fk_batch_base_ex(ctr_fk_handle h, const double* jv_base, const double* jv_guess, int64_t B, int mode, double step,
+                         int32_t nsamples, double tol, int32_t max_iter, uint32_t flags, double* jv_tip, double* tip,
+                         int32_t* iters, int32_t* status, double* resid, void* stream)
+{
     int rc = check_common(h, jv_base, B, mode, step, nsamples);
     if (rc) return rc;
-    if ((rc = check_align(h, jv_base, tip, nullptr)) || (rc = check_align(h, jv_tip, nullptr, nullptr))) return rc;
+    if ((rc = check_align(h, jv_base, tip, nullptr)) || (rc = check_align(h, jv_tip, nullptr, nullptr)) ||
+        (rc = check_align(h, jv_guess, nullptr, nullptr))) return rc;
+    if (flags & ~(uint32_t)CTR_FK_FLAG_RK4) { set_error("ctr_fk_batch_base_ex: unknown flag (CTR_FK_FLAG_RK4 only)"); return CTR_FK_E_ARG; }
     if (B > 0 && !jv_tip) { set_error("jv_tip output is required"); return CTR_FK_E_NULL; }
     if (!(tol > 0.0) || !std::isfinite(tol) || max_iter < 1) { set_error("tol must be > 0 and max_iter >= 1"); return CTR_FK_E_ARG; }
     if (B == 0) return 0;
@@ -885,6 +895,7 @@ int ctr_fk_batch_base(ctr_fk_handle h, const double* jv_base, int64_t B, int mod
         ShootArgs a;
         a.jv_base = jv_base; a.B = B; a.mode = mode; a.step = step; a.nsamples = nsamples; a.tol = tol;
         a.max_iter = max_iter; a.order = order; a.jv_tip = jv_tip; a.iters = iters; a.status = status; a.ticket = ticket;
+        a.jv_guess = jv_guess; a.resid = resid; a.rk4 = (flags & CTR_FK_FLAG_RK4) ? 1 : 0;
         e = launch_shoot(h->key, h->rb, a, h->sm_count, st);
     }
     if (order) cudaFreeAsync(order, st);

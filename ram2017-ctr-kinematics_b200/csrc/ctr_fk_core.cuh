@@ -1196,35 +1196,315 @@ CTR_HD bool solve_small(double* J, double* f)
     return true;
 }
 
-// One Newton iteration of the base-angle shooting problem.  q holds the joint vector with the
-// CURRENT tip-angle estimate; beta[t] the wanted base angles (t >= 1).  Returns the residual
-// max-norm BEFORE the update; q's tip angles are updated in place unless converged.
-// status: 0 running / converged decided by the caller, 2 = singular Jacobian, 1 = phi out of range
+// ---- the same operator on the continuum model, integrated by classical RK4 -----------------------------------
+// The reference's sweep is explicit Euler (tip -> base, step h) on the torsional rod equations:
+//     d alpha_t / d sigma = z_t - z_0                    (t >= 1; alpha_0 = 0: all angles are relative to tube 0)
+//     d z_t / d sigma     = (1 + nu_t) kappa_sec(t) x_t   (t <= T-2, inside the curved interval of its section)
+//     z_{T-1}             = -cl sum_{t < T-1} czc_t z_t   (torque balance)
+//     x_t = cos alpha_t cx + sin alpha_t cy,  (cx, cy) = sum_t' g_sec(t') (-sin alpha_t', cos alpha_t') / K_active
+// with sigma the arc length from the tip.  CTR_FK_FLAG_RK4 integrates this system with the fixed-step fourth-order
+// Runge-Kutta scheme over the same N-1 steps (split where the right-hand side jumps, see sweep_tangent_rk4) and carries
+// the tangent-linear system (the variational equations, d state / d tip angles) through every stage, so Newton's method
+// again sees the exact derivative of the discrete map.
+// It is a DIFFERENT discretisation from the reference's: its base angles differ from the reference sweep's by O(h)
+// (tests/test_kernel_logic_cpu.py::test_rk4_sweep_converges_to_the_reference_sweep); there is no parity claim for it,
+// its checker is oracle/ctr_shoot_rk4_py.py.  Tube 0's own joint angle (which the reference lets act on the tip-most
+// sample only, section_i.h:308) is taken as 0 throughout.
 template <class L>
-CTR_HD double shoot_iteration(const KRobot& rb, double* q, const double* beta, int mode, double step,
-                              int nsamples, double tol, int& status)
-{
-    constexpr int T = L::T, U = (T > 1 ? T - 1 : 1);
-    Ctl<L> c;
-    setup_control<L>(rb, q, mode, step, nsamples, c);
-    if (c.status) { status = 1; return 0.0; }
-    double base[T], J[U * U], f[U];
-    sweep_tangent<L>(rb, c, base, T > 1 ? J : nullptr);
-    double res = 0.0;
+struct Rk4Rhs {
+    static constexpr int S = L::S, T = L::T, U = (T > 1 ? T - 1 : 1);
+    // y = (alpha_1..alpha_{T-1}, z_0..z_{T-2}); Y[i][j] = d y_i / d alpha_tip[j+1]
+    static CTR_HD void eval(const KRobot& rb, const Ctl<L>& c, double pos, const double* y, const double (*Y)[U],
+                            double* dy, double (*dY)[U])
+    {
+        bool in_k[S], in_c[S];
+        const double p = pos > 0.0 ? pos : 0.0;
 #pragma unroll
-    for (int r = 0; r + 1 < T; ++r) { f[r] = base[r + 1] - beta[r + 1]; res = fmax(res, fabs(f[r])); }
-    if (T == 1 || res <= tol) return res;
-    if (!solve_small<U>(J, f)) { status = 2; return res; }
-    // step limiter: tube angles are periodic, a Newton step larger than 1 rad is an overshoot
+        for (int s = 0; s < S; ++s) {
+            in_k[s] = (s == S - 1) ? true : (p <= c.end[s]);
+            in_c[s] = in_k[s] && (c.start[s] <= p);
+        }
+        double rks = rb.rk[S - 1];
 #pragma unroll
-    for (int r = 0; r + 1 < T; ++r) {
-        const double d = fmin(1.0, fmax(-1.0, f[r]));
-        const int t = r + 1;
-        const int j = 2 + L::sec_of(t) + t;
-        q[j] = q[j] - d;
+        for (int s = S - 2; s >= 0; --s) rks = in_k[s] ? rb.rk[s] : rks;
+        double sn[T], cs[T];
+        sn[0] = 0.0; cs[0] = 1.0;
+#pragma unroll
+        for (int t = 1; t < T; ++t) fast_sincos(y[t - 1], sn[t], cs[t]);
+        double cx = 0.0, cy = 0.0, dcx[U], dcy[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { dcx[j] = 0.0; dcy[j] = 0.0; }
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const double g = in_c[L::sec_of(t)] ? rb.kg[L::sec_of(t)] * rks : 0.0;
+            cx = x_fma(-sn[t], g, cx);
+            cy = x_fma(cs[t], g, cy);
+            if (t >= 1) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    dcx[j] = x_fma(-cs[t] * g, Y[t - 1][j], dcx[j]);
+                    dcy[j] = x_fma(-sn[t] * g, Y[t - 1][j], dcy[j]);
+                }
+            }
+        }
+        // z of the innermost tube from the balance
+        double zi = 0.0, dzi[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) dzi[j] = 0.0;
+        if (T > 1) {
+#pragma unroll
+            for (int t = 0; t + 1 < T; ++t) {
+                zi = x_fma(rb.czc[t], y[U + t], zi);
+#pragma unroll
+                for (int j = 0; j < U; ++j) dzi[j] = x_fma(rb.czc[t], Y[U + t][j], dzi[j]);
+            }
+            zi = -zi * rb.cl;
+#pragma unroll
+            for (int j = 0; j < U; ++j) dzi[j] = -dzi[j] * rb.cl;
+        }
+        const double z0 = y[U];
+#pragma unroll
+        for (int t = 1; t < T; ++t) {
+            const double zt = (t == T - 1) ? zi : y[U + t];
+            dy[t - 1] = zt - z0;
+#pragma unroll
+            for (int j = 0; j < U; ++j) dY[t - 1][j] = ((t == T - 1) ? dzi[j] : Y[U + t][j]) - Y[U][j];
+        }
+#pragma unroll
+        for (int t = 0; t + 1 < T; ++t) {
+            const double w  = in_c[L::sec_of(t)] ? rb.onu[t] * rb.kappa[L::sec_of(t)] : 0.0;
+            const double ux = x_fma(cs[t], cx, sn[t] * cy);
+            const double uy = x_fma(cs[t], cy, -(sn[t] * cx));          // d ux / d alpha_t
+            dy[U + t] = w * ux;
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                dY[U + t][j] = w * x_fma(uy, (t >= 1 ? Y[t - 1][j] : 0.0), x_fma(cs[t], dcx[j], sn[t] * dcy[j]));
+        }
     }
-    return res;
+};
+
+// One classical RK4 step of length hs (towards the base) with the interval masks frozen at arc position pm.
+template <class L>
+CTR_HD void rk4_substep(const KRobot& rb, const Ctl<L>& c, double pm, double hs, double* y,
+                        double (*Y)[(L::T > 1 ? L::T - 1 : 1)])
+{
+    constexpr int T = L::T, U = (T > 1 ? T - 1 : 1), M = 2 * U;
+    double ya[M], Ya[M][U], yt[M], Yt[M][U], dy[M], dY[M][U];
+    // stage 1
+    Rk4Rhs<L>::eval(rb, c, pm, y, Y, dy, dY);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        ya[i] = dy[i]; yt[i] = x_fma(0.5 * hs, dy[i], y[i]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) { Ya[i][j] = dY[i][j]; Yt[i][j] = x_fma(0.5 * hs, dY[i][j], Y[i][j]); }
+    }
+    // stages 2 and 3 (midpoint)
+#pragma unroll 1
+    for (int stage = 2; stage <= 3; ++stage) {
+        const double hn = (stage == 2) ? 0.5 * hs : hs;
+        Rk4Rhs<L>::eval(rb, c, pm, yt, Yt, dy, dY);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            ya[i] = x_fma(2.0, dy[i], ya[i]); yt[i] = x_fma(hn, dy[i], y[i]);
+#pragma unroll
+            for (int j = 0; j < U; ++j) { Ya[i][j] = x_fma(2.0, dY[i][j], Ya[i][j]); Yt[i][j] = x_fma(hn, dY[i][j], Y[i][j]); }
+        }
+    }
+    // stage 4
+    Rk4Rhs<L>::eval(rb, c, pm, yt, Yt, dy, dY);
+    const double w = hs * (1.0 / 6.0);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        y[i] = x_fma(w, ya[i] + dy[i], y[i]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) Y[i][j] = x_fma(w, Ya[i][j] + dY[i][j], Y[i][j]);
+    }
 }
+
+// The right-hand side jumps where a section's curved interval starts or ends (<= 2S arc positions, off the sample
+// grid in general).  A Runge-Kutta step across a jump is only first-order accurate, which would leave the whole sweep
+// at the accuracy of the reference's Euler sweep; so a step that contains such a position is split there, each part
+// integrated with the masks of its own side (taken at its midpoint).  The sweep is then fourth-order in h.
+template <class L>
+CTR_HD void sweep_tangent_rk4(const KRobot& rb, const Ctl<L>& c, double* base, double* jac)
+{
+    constexpr int S = L::S, T = L::T, U = (T > 1 ? T - 1 : 1), M = 2 * U;
+    double y[M], Y[M][U];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        y[i] = (i < U && i + 1 < T) ? c.al[i + 1] : 0.0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) Y[i][j] = (i == j && i + 1 < T) ? 1.0 : 0.0;
+    }
+    if (T > 1) {
+        double pos = c.arc_end;
+#pragma unroll 1
+        for (int k = c.n - 1; k >= 1; --k) {
+            const double stop = x_sub(pos, c.h);
+            double cur = pos;
+#pragma unroll 1
+            while (cur > stop) {
+                double nb = stop;                       // the nearest switching position strictly inside (stop, cur)
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (c.end[s] < cur && c.end[s] > nb) nb = c.end[s];
+                    if (c.start[s] < cur && c.start[s] > nb) nb = c.start[s];
+                }
+                const double hs = cur - nb;
+                rk4_substep<L>(rb, c, cur - 0.5 * hs, hs, y, Y);
+                cur = nb;
+            }
+            pos = stop;
+        }
+    }
+    base[0] = 0.0;
+#pragma unroll
+    for (int t = 1; t < T; ++t) base[t] = y[t - 1];
+    if (jac) {
+#pragma unroll
+        for (int r = 0; r + 1 < T; ++r)
+#pragma unroll
+            for (int j = 0; j + 1 < T; ++j) jac[r * (T - 1) + j] = Y[r][j];
+    }
+}
+
+// Per-configuration state of the base-angle shooting solve: damped Newton on  base(x) - beta = 0  for the tip angles x
+// of tubes 1..T-1.  round() runs ONE sweep (with its tangent) at the current trial point — the unit of lock-step work
+// of the persistent kernel — and returns kRunning or a final CTR_FK_SHOOT_* status:
+//   * the trial point x_acc - lam d is accepted when it lowers the residual max-norm (Armijo: below
+//     (1 - 1e-4 lam) res_acc); then the Newton direction d = J^-1 f is taken from its own Jacobian (step limiter 1 rad:
+//     tube angles are periodic, a longer step is an overshoot) and lam returns to 1;
+//   * a rejected trial halves lam (backtracking line search); more than max_reject rejections in a row mean the
+//     residual has stopped decreasing (a fold of the base-angle map: no root on this branch);
+//   * with a guess from the caller (warm start / branch tracking) that ends the solve: CTR_FK_SHOOT_STALLED after a
+//     handful of sweeps — a lane holding such an input gives its slot back instead of running to the sweep cap, and the
+//     solve never leaves the branch the caller named;
+//   * without a guess the first start is x = beta, and a start that stalls (or meets a singular Jacobian) is followed by
+//     another from x = beta + u, u uniform in [-pi, pi)^(T-1) (counter-based, keyed by beta: reproducible wherever the
+//     configuration is solved), until a root is found or max_iter sweeps are spent.  These robots have several roots
+//     for many inputs, so WHICH root comes back is then arbitrary; measured on the shipped robots (3000 random inputs
+//     with a root, N = 128, cap 100): 99.8 / 100 / 100 / 99.3 % solved at a mean of 6.6 / 5.7 / 6.5 / 10.6 sweeps
+//     (plain Newton from x = beta: 96 / 97 / 96 / 88 %);
+//   * the alpha slots of q return the ACCEPTED estimate with the lowest residual over all starts, whatever the status.
+template <class L, bool RK4>
+struct ShootState {
+    static constexpr int T = L::T, U = (T > 1 ? T - 1 : 1), NJ = L::NJ;
+    static constexpr int kRunning = -1, kMaxRejectGuess = 5, kMaxRejectFree = 1;
+    double q[NJ], beta[T], d[U], best[U];
+    double res, lam, best_res;
+    int    it, nrej, max_reject;
+    bool   fresh, restarts;
+
+    // jv_base: joint vector with the WANTED base angles in its alpha slots; guess (nullable): joint vector whose alpha
+    // slots hold the starting tip angles (warm start: the previous configuration's solution); default x = beta
+    CTR_HD void start(const double* jv_base, const double* guess)
+    {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) q[j] = jv_base[j];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = 2 + L::sec_of(t) + t;
+            beta[t] = jv_base[j];
+            if (guess && t >= 1) q[j] = guess[j];
+        }
+#pragma unroll
+        for (int r = 0; r < U; ++r) { d[r] = 0.0; best[r] = q[2 + L::sec_of(r + 1 < T ? r + 1 : 0) + (r + 1 < T ? r + 1 : 0)]; }
+        res = 0.0; lam = 1.0; it = 0; nrej = 0; fresh = true;
+        best_res = -1.0;                                          // nothing accepted yet
+        restarts = (guess == nullptr);                            // a caller who names the branch stays on it
+        max_reject = guess ? kMaxRejectGuess : kMaxRejectFree;
+    }
+    // this start has failed (stall or singular Jacobian): remember it if it is the best so far, then either begin
+    // again from another point or finish with `st`
+    CTR_HD int fail(int st, int max_iter)
+    {
+        keep_best();
+        if (!restarts || it >= max_iter) { restore_best(); return st; }
+        // x = beta + u, u uniform in [-pi, pi)^U from a counter-based generator keyed by the wanted angles, so the
+        // result does not depend on which lane or device solves the configuration
+        unsigned long long key = 0x9e3779b97f4a7c15ull * (unsigned long long)(it + 1);
+#pragma unroll
+        for (int t = 1; t < T; ++t) key = shoot_mix(key ^ shoot_bits(beta[t]));
+#pragma unroll
+        for (int t = 1; t < T; ++t) {
+            key = shoot_mix(key + 0x9e3779b97f4a7c15ull);
+            const double u = (double)(key >> 11) * (1.0 / 9007199254740992.0);       // [0, 1)
+            q[2 + L::sec_of(t) + t] = beta[t] + (u - 0.5) * 6.283185307179586;
+        }
+        lam = 1.0; nrej = 0; fresh = true;
+        return kRunning;
+    }
+    CTR_HD void keep_best()
+    {
+        if (!fresh && (best_res < 0.0 || res < best_res)) {
+            best_res = res;
+#pragma unroll
+            for (int r = 0; r + 1 < T; ++r) best[r] = q[2 + L::sec_of(r + 1) + (r + 1)];
+        }
+    }
+    CTR_HD void restore_best()
+    {
+        if (best_res >= 0.0) {
+            res = best_res;
+#pragma unroll
+            for (int r = 0; r + 1 < T; ++r) q[2 + L::sec_of(r + 1) + (r + 1)] = best[r];
+        }
+    }
+    static CTR_HD unsigned long long shoot_mix(unsigned long long z)              // splitmix64 finaliser
+    {
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    }
+    static CTR_HD unsigned long long shoot_bits(double x)
+    {
+#ifdef __CUDA_ARCH__
+        return (unsigned long long)__double_as_longlong(x);
+#else
+        union { double d; unsigned long long u; } v; v.d = x; return v.u;
+#endif
+    }
+    CTR_HD int round(const KRobot& rb, int mode, double step, int nsamples, double tol, int max_iter)
+    {
+        double qt[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) qt[j] = q[j];
+        if (!fresh) {
+#pragma unroll
+            for (int r = 0; r + 1 < T; ++r) {
+                const int j = 2 + L::sec_of(r + 1) + (r + 1);
+                qt[j] = q[j] - lam * d[r];
+            }
+        }
+        Ctl<L> c;
+        setup_control<L>(rb, qt, mode, step, nsamples, c);
+        if (c.status) return 1;                                   // CTR_FK_SHOOT_PHI_RANGE
+        double base[T], J[U * U], f[U];
+        if (RK4) sweep_tangent_rk4<L>(rb, c, base, T > 1 ? J : nullptr);
+        else     sweep_tangent<L>(rb, c, base, T > 1 ? J : nullptr);
+        ++it;
+        if (T == 1) { res = 0.0; return 0; }
+        double r_new = 0.0;
+#pragma unroll
+        for (int r = 0; r + 1 < T; ++r) { f[r] = base[r + 1] - beta[r + 1]; r_new = fmax(r_new, fabs(f[r])); }
+        const bool accept = fresh || (r_new < res * (1.0 - 1e-4 * lam));      // false for a NaN residual
+        if (accept) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) q[j] = qt[j];
+            res = r_new; nrej = 0; fresh = false;
+            if (r_new <= tol) return 0;                           // CTR_FK_SHOOT_OK
+            if (!(r_new == r_new) || !solve_small<U>(J, f)) return fail(2, max_iter);     // CTR_FK_SHOOT_SINGULAR
+#pragma unroll
+            for (int r = 0; r < U; ++r) d[r] = fmin(1.0, fmax(-1.0, f[r]));
+            lam = 1.0;
+        } else {
+            lam *= 0.5;
+            if (++nrej > max_reject) return fail(4, max_iter);    // CTR_FK_SHOOT_STALLED (or start again)
+        }
+        if (it >= max_iter) { keep_best(); restore_best(); return 3; }        // CTR_FK_SHOOT_MAX_ITER
+        return kRunning;
+    }
+};
 
 // ---- rigid transform as (unit quaternion, translation): used by the warp-parallel backbone pass
 struct QT {

@@ -11,26 +11,27 @@ cudaError_t launch_stability(int key, const KRobot& rb, const StabArgs& a, int s
 }
 
 // ---- base-angle shooting solve ----------------------------------------------
-// Newton iterations per configuration vary (mean ~5, tail beyond 50 near bifurcations).  The
-// kernel is persistent: grid = resident CTAs of the device; every lane owns one configuration at a
-// time and, when it converges, draws the next index from a global ticket counter (one atomicAdd
-// per warp and refill round, ranks by ballot).  All lanes of a warp execute one Newton iteration
-// (one tangent-linear sweep, uniform trip count in fixed-N mode) per round, so nobody waits for a
-// slow neighbour to finish all of its iterations.
-template <class L>
+// Sweeps per configuration vary (2-3 from a nearby guess, ~6 from the naive start x = beta, a handful more where the
+// line search has to backtrack).  The kernel is persistent: grid = resident CTAs of the device; every lane owns one
+// configuration at a time and, when it finishes, draws the next index from a global ticket counter (one atomicAdd
+// per warp and refill round, ranks by ballot).  All lanes of a warp execute one round of the damped Newton iteration
+// (ShootState::round: one tangent-linear sweep, uniform trip count in fixed-N mode), so nobody waits for a
+// slow neighbour to finish all of its rounds.
+template <class L, bool RK4>
 __global__ void __launch_bounds__(kBlock)
 fk_shoot_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ ShootArgs a)
 {
-    constexpr int T = L::T, NJ = L::NJ;
+    constexpr int NJ = L::NJ;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     int64_t cfg = -1;
-    int     it = 0;
-    double  q[NJ], beta[T];
+    ShootState<L, RK4> s;
+    {
+        double zero[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) q[j] = 0.0;
-#pragma unroll
-    for (int t = 0; t < T; ++t) beta[t] = 0.0;
+        for (int j = 0; j < NJ; ++j) zero[j] = 0.0;
+        s.start(zero, nullptr);
+    }
     bool drained = false;                                   // queue exhausted (warp-uniform)
     for (;;) {
         // ---- refill idle lanes from the ticket queue ---------------------------------------------
@@ -45,29 +46,24 @@ fk_shoot_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Shoot
                 const int64_t idx = (int64_t)first + __popc(m & ((1u << lane) - 1u));
                 if (idx < a.B) {
                     cfg = a.order ? (int64_t)a.order[idx] : idx;
-                    load_jv<L>(a.jv_base, cfg, q);
-#pragma unroll
-                    for (int t = 0; t < T; ++t) beta[t] = q[2 + L::sec_of(t) + t];
-                    it = 0;
+                    double qb[NJ], qg[NJ];
+                    load_jv<L>(a.jv_base, cfg, qb);
+                    if (a.jv_guess) load_jv<L>(a.jv_guess, cfg, qg);
+                    s.start(qb, a.jv_guess ? qg : nullptr);
                 }
             }
             if ((int64_t)first + __popc(m) >= a.B) drained = true;
         }
         if (__ballot_sync(full, cfg >= 0) == 0) break;       // nothing left for this warp
-        // ---- one Newton iteration on every busy lane ---------------------------------------------
+        // ---- one sweep (one damped-Newton round) on every busy lane --------------------------------
         if (cfg >= 0) {
-            int st = 0;
-            const double res = shoot_iteration<L>(rb, q, beta, a.mode, a.step, a.nsamples, a.tol, st);
-            bool done = false;
-            if (st) done = true;
-            else if (res <= a.tol) done = true;
-            else if (it + 1 >= a.max_iter) { st = 3; ++it; done = true; }
-            else ++it;
-            if (done) {
+            const int st = s.round(rb, a.mode, a.step, a.nsamples, a.tol, a.max_iter);
+            if (st != ShootState<L, RK4>::kRunning) {
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) a.jv_tip[cfg * NJ + j] = q[j];
-                if (a.iters) a.iters[cfg] = it;
+                for (int j = 0; j < NJ; ++j) a.jv_tip[cfg * NJ + j] = s.q[j];
+                if (a.iters) a.iters[cfg] = s.it;
                 if (a.status) a.status[cfg] = st;
+                if (a.resid) a.resid[cfg] = (st == 1) ? __longlong_as_double(0x7ff8000000000000ll) : s.res;
                 cfg = -1;
             }
         }
@@ -82,12 +78,14 @@ cudaError_t launch_shoot(int key, const KRobot& rb, const ShootArgs& a, int sm_c
 #define X(S, A, Bq, C) \
     case S * 1000 + A * 100 + Bq * 10 + C: { \
         int per_sm = 0; \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_shoot_kernel<Lay<S, A, Bq, C>>, kBlock, 0); \
+        e = a.rk4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_shoot_kernel<Lay<S, A, Bq, C>, true>, kBlock, 0) \
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk_shoot_kernel<Lay<S, A, Bq, C>, false>, kBlock, 0); \
         if (e != cudaSuccess) return e; \
         if (per_sm < 1) per_sm = 1; \
         int64_t want = (a.B + kBlock - 1) / kBlock; \
         int64_t cap = (int64_t)per_sm * sm_count; \
-        fk_shoot_kernel<Lay<S, A, Bq, C>><<<(unsigned)(want < cap ? want : cap), kBlock, 0, st>>>(rb, a); \
+        if (a.rk4) fk_shoot_kernel<Lay<S, A, Bq, C>, true><<<(unsigned)(want < cap ? want : cap), kBlock, 0, st>>>(rb, a); \
+        else       fk_shoot_kernel<Lay<S, A, Bq, C>, false><<<(unsigned)(want < cap ? want : cap), kBlock, 0, st>>>(rb, a); \
         break; }
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X

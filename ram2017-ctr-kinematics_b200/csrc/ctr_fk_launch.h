@@ -75,6 +75,9 @@ struct ShootArgs {
     int32_t*            iters;      // nullable
     int32_t*            status;     // nullable
     unsigned long long* ticket;     // zero-initialised work counter
+    const double*       jv_guess;   // [B][NJ] nullable: starting tip angles (warm start)
+    double*             resid;      // [B] nullable: residual max-norm at the returned tip angles
+    int                 rk4;        // CTR_FK_FLAG_RK4: continuum model integrated by RK4 instead of the reference sweep
 };
 
 constexpr int kBlock = 128;     // threads per CTA for every solver kernel

@@ -18,12 +18,13 @@ FLAG_JAC_GIVEN_POSES = 0x100
 FLAG_GATHER_MULTICAST = 0x200
 FLAG_GATHER_ROWWISE = 0x400
 FLAG_HOST_STAGED = 0x800
+FLAG_RK4 = 0x1000
 HOST_WRITE_COMBINED = 1
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
 SCALE_NONE, SCALE_GAMMA, SCALE_PROPORTIONAL = 0, 1, 2
-SHOOT_OK, SHOOT_PHI_RANGE, SHOOT_SINGULAR, SHOOT_MAX_ITER = 0, 1, 2, 3
+SHOOT_OK, SHOOT_PHI_RANGE, SHOOT_SINGULAR, SHOOT_MAX_ITER, SHOOT_STALLED = 0, 1, 2, 3, 4
 
 
 class SectionDesc(C.Structure):
@@ -92,6 +93,8 @@ SYMBOLS = {
     "ctr_fk_stability_host_ex": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_uint32, _P, _P]),
     "ctr_fk_batch_base": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_double, C.c_int32,
                                     _P, _P, _P, _P, _P]),
+    "ctr_fk_batch_base_ex": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_double, C.c_int32, C.c_double, C.c_int32,
+                                       C.c_uint32, _P, _P, _P, _P, _P, _P]),
     "ctr_fk_sample_joints": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, _P, _P]),
     "ctr_fk_sample_joints_scaled": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
                                               C.c_int32, _P, _P]),
@@ -309,10 +312,11 @@ class Engine:
         _check(load().ctr_fk_stability_batch_ex(self.handle, _ptr(jv), B, angle_step, arc_step, min_degree, flags,
                                                 _ptr(stable), _ptr(degree), stream))
 
-    def batch_base(self, jv_base, B, mode, step=0.0, nsamples=0, tol=1e-11, max_iter=24, jv_tip=None, tip=None,
-                   iters=None, status=None, stream=None):
-        _check(load().ctr_fk_batch_base(self.handle, _ptr(jv_base), B, mode, step, nsamples, tol, max_iter,
-                                        _ptr(jv_tip), _ptr(tip), _ptr(iters), _ptr(status), stream))
+    def batch_base(self, jv_base, B, mode, step=0.0, nsamples=0, tol=1e-11, max_iter=100, jv_tip=None, tip=None,
+                   iters=None, status=None, stream=None, jv_guess=None, resid=None, flags=0):
+        """ctr_fk_batch_base_ex; flags: FLAG_RK4.  jv_guess=None starts from x = beta (with restarts)."""
+        _check(load().ctr_fk_batch_base_ex(self.handle, _ptr(jv_base), _ptr(jv_guess), B, mode, step, nsamples, tol, max_iter,
+                                           flags, _ptr(jv_tip), _ptr(tip), _ptr(iters), _ptr(status), _ptr(resid), stream))
 
     def sample_joints(self, seed, first, B, jv, stream=None, policy=SCALE_NONE, p0=1.0, p1=1.0, lut_size=0):
         _check(load().ctr_fk_sample_joints_scaled(self.handle, seed, first, B, policy, p0, p1, lut_size,

@@ -3,6 +3,7 @@
 // so that their logic can be compared with the oracle in a container without a GPU.  Not part of
 // the product: libctrfk.so has no CPU path and never links this file.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/ctr_fk.h"
@@ -91,38 +92,40 @@ extern "C" void hostsim_se3(double ux, double uy, double uz, double h, double* s
     se3_step_fast(ux, uy, uz, h, 1e-12, fast7[0], fast7[1], fast7[2], fast7[3], fast7[4], fast7[5], fast7[6]);
 }
 
-// Base-angle shooting on the CPU build of the device code: jv_base holds base angles in the alpha
-// slots; returns tip-angle joint vectors in jv_tip, iteration counts and status.
+// Base-angle shooting on the CPU build of the device code (ShootState: damped Newton, one sweep per round):
+// jv_base holds base angles in the alpha slots, jv_guess (nullable) the starting tip angles; returns tip-angle
+// joint vectors in jv_tip, sweep counts, status and the residual at the returned angles.
 namespace {
-template <class L>
-void shoot_run(const KRobot& rb, const double* jvb, int64_t B, int mode, double step, int ns, double tol, int maxit,
-               double* jv_tip, int32_t* iters, int32_t* status)
+template <class L, bool RK4>
+void shoot_run(const KRobot& rb, const double* jvb, const double* guess, int64_t B, int mode, double step, int ns,
+               double tol, int maxit, double* jv_tip, int32_t* iters, int32_t* status, double* resid)
 {
     for (int64_t i = 0; i < B; ++i) {
-        double q[L::NJ], beta[L::T];
-        for (int j = 0; j < L::NJ; ++j) q[j] = jvb[i * L::NJ + j];
-        for (int t = 0; t < L::T; ++t) beta[t] = q[2 + L::sec_of(t) + t];
-        int st = 0, it = 0;
-        for (;; ++it) {
-            double res = shoot_iteration<L>(rb, q, beta, mode, step, ns, tol, st);
-            if (st) break;
-            if (res <= tol) break;
-            if (it + 1 >= maxit) { st = 3; ++it; break; }
-        }
-        for (int j = 0; j < L::NJ; ++j) jv_tip[i * L::NJ + j] = q[j];
-        iters[i] = it; status[i] = st;
+        ShootState<L, RK4> s;
+        s.start(jvb + i * L::NJ, guess ? guess + i * L::NJ : nullptr);
+        if (const char* e = std::getenv("HOSTSIM_SHOOT_MAX_REJECT")) s.max_reject = std::atoi(e);
+        if (const char* e = std::getenv("HOSTSIM_SHOOT_RESTARTS")) s.restarts = !guess && std::atoi(e) != 0;
+        int st;
+        while ((st = s.round(rb, mode, step, ns, tol, maxit)) == ShootState<L, RK4>::kRunning) {}
+        for (int j = 0; j < L::NJ; ++j) jv_tip[i * L::NJ + j] = s.q[j];
+        iters[i] = s.it; status[i] = st;
+        if (resid) resid[i] = s.res;
     }
 }
 }  // namespace
 
-extern "C" int hostsim_shoot(const ctr_robot_desc* d, const double* jvb, int64_t B, int mode, double step, int ns,
-                             double tol, int maxit, double* jv_tip, int32_t* iters, int32_t* status)
+extern "C" int hostsim_shoot(const ctr_robot_desc* d, const double* jvb, const double* guess, int64_t B, int mode,
+                             double step, int ns, double tol, int maxit, int rk4, double* jv_tip, int32_t* iters,
+                             int32_t* status, double* resid)
 {
     KRobot rb;
     int rc = make_krobot(d, &rb);
     if (rc) return rc;
     switch (layout_key(d)) {
-#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: shoot_run<Lay<S, A, Bq, C>>(rb, jvb, B, mode, step, ns, tol, maxit, jv_tip, iters, status); break;
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: \
+        if (rk4) shoot_run<Lay<S, A, Bq, C>, true>(rb, jvb, guess, B, mode, step, ns, tol, maxit, jv_tip, iters, status, resid); \
+        else     shoot_run<Lay<S, A, Bq, C>, false>(rb, jvb, guess, B, mode, step, ns, tol, maxit, jv_tip, iters, status, resid); \
+        break;
         CTRK_FOR_EACH_LAYOUT(X)
 #undef X
         default: return CTR_FK_E_DESC;
@@ -133,24 +136,25 @@ extern "C" int hostsim_shoot(const ctr_robot_desc* d, const double* jvb, int64_t
 // tangent-linear sweep of one configuration: base angles and d base / d tip angles
 namespace {
 template <class L>
-int tangent_run(const KRobot& rb, const double* jv, int mode, double step, int ns, double* base, double* jac)
+int tangent_run(const KRobot& rb, const double* jv, int mode, double step, int ns, int rk4, double* base, double* jac)
 {
     Ctl<L> c;
     setup_control<L>(rb, jv, mode, step, ns, c);
     if (c.status) return 1;
-    sweep_tangent<L>(rb, c, base, L::T > 1 ? jac : nullptr);
+    if (rk4) sweep_tangent_rk4<L>(rb, c, base, L::T > 1 ? jac : nullptr);
+    else     sweep_tangent<L>(rb, c, base, L::T > 1 ? jac : nullptr);
     return 0;
 }
 }  // namespace
 
-extern "C" int hostsim_tangent(const ctr_robot_desc* d, const double* jv, int mode, double step, int ns,
+extern "C" int hostsim_tangent(const ctr_robot_desc* d, const double* jv, int mode, double step, int ns, int rk4,
                                double* base, double* jac)
 {
     KRobot rb;
     int rc = make_krobot(d, &rb);
     if (rc) return rc;
     switch (layout_key(d)) {
-#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: return tangent_run<Lay<S, A, Bq, C>>(rb, jv, mode, step, ns, base, jac);
+#define X(S, A, Bq, C) case S * 1000 + A * 100 + Bq * 10 + C: return tangent_run<Lay<S, A, Bq, C>>(rb, jv, mode, step, ns, rk4, base, jac);
         CTRK_FOR_EACH_LAYOUT(X)
 #undef X
         default: return CTR_FK_E_DESC;

@@ -131,32 +131,190 @@ def test_f32_solver_logic(ctrfk, oracle, hostsim, robots, name):
                 assert dp.max() < TOL_F32_POS and ang.max() < TOL_F32_ROT, ("packed", dp.max(), ang.max())
 
 
+def _hostsim_shoot(hostsim, d, jvb, mode, guess=None, step=0.0, nsamples=0, tol=1e-11, max_iter=60, rk4=0):
+    import ctypes as C
+    B = jvb.shape[0]
+    jt = np.zeros_like(jvb); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32); res = np.zeros(B)
+    rc = hostsim.hostsim_shoot(C.addressof(d), jvb.ctypes.data, None if guess is None else guess.ctypes.data, B, mode,
+                               step, nsamples, tol, max_iter, rk4, jt.ctypes.data, it.ctypes.data, st.ctypes.data,
+                               res.ctypes.data)
+    assert rc == 0
+    return jt, it, st, res
+
+
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
 def test_shooting_solve_logic(ctrfk, oracle, hostsim, robots, name):
-    """Base-angle shooting, CPU build of the device code.  Its checker is the
-    reference sweep itself: the oracle, run at the tip angles found, must end at the wanted base
-    angles.  Inputs are base angles produced by the oracle from random tip angles, so a root
-    exists; robots this curved have several roots for many inputs, so the root found need not be
-    the one the input came from."""
-    import ctypes as C
+    """Base-angle shooting, CPU build of the device code (ShootState: damped Newton with a
+    backtracking line search, one sweep per round).  Its checker is the reference sweep itself: the oracle, run at
+    the tip angles found, must end at the wanted base angles.  Inputs are base angles produced by the oracle from
+    random tip angles, so a root exists; robots this curved have several roots for many inputs, so from the naive
+    start x = beta the root found need not be the one the input came from."""
     d = robots[name]
     B = 400
     jv = ctrfk.sample_joints_host(d, 77, 0, B)
     o = oracle.fk_batch(d, jv, ctrfk.MODE_NSAMPLE, nsamples=128)
     jvb = util.base_angle_inputs(d, jv, o["alpha_base"])
-    jt = np.zeros_like(jv); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
-    rc = hostsim.hostsim_shoot(C.addressof(d), jvb.ctypes.data, B, ctrfk.MODE_NSAMPLE, 0.0, 128, 1e-11, 60,
-                               jt.ctypes.data, it.ctypes.data, st.ctypes.data)
-    assert rc == 0
+    jt, it, st, res = _hostsim_shoot(hostsim, d, jvb, ctrfk.MODE_NSAMPLE, nsamples=128, max_iter=100)
     ok = st == 0
-    assert ok.mean() > 0.85 and set(np.unique(st)) <= {0, 2, 3}
+    assert ok.mean() >= 0.98 and set(np.unique(st)) <= {0, 3, 4}     # restarts: see ShootState
     o2 = oracle.fk_batch(d, jt, ctrfk.MODE_NSAMPLE, nsamples=128)
-    res = np.abs(o2["alpha_base"][:, 1:] - o["alpha_base"][:, 1:]).max(axis=1)
-    assert res[ok].max() < 1e-10                       # the reference sweep confirms every root
-    assert it[ok].max() > it[ok].min() + 5             # iteration counts really diverge
+    r2 = np.abs(o2["alpha_base"][:, 1:] - o["alpha_base"][:, 1:]).max(axis=1)
+    assert r2[ok].max() < 1e-10                       # the reference sweep confirms every root
+    assert np.abs(r2 - res).max() < 1e-9               # ... and the residual reported for every configuration, root or not
+    assert it[ok].max() > it[ok].min() + 3             # sweep counts really diverge
+    assert it.mean() < 14.0                            # restarts are paid for by the few configurations that need them
     idx = util.alpha_indices(d)
-    assert np.array_equal(jt[:, [i for i in range(jv.shape[1]) if i not in idx[1:]]],
-                          jv[:, [i for i in range(jv.shape[1]) if i not in idx[1:]]])   # only alphas 1.. change
+    keep = [i for i in range(jv.shape[1]) if i not in idx[1:]]
+    assert np.array_equal(jt[:, keep], jv[:, keep])    # only alphas 1.. change
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_shooting_solve_warm_start_recovers_the_branch(ctrfk, oracle, hostsim, robots, name):
+    """Branch tracking: started from a guess near the tip angles the base angles came from (what a controller has
+    from the previous cycle), the solve must return THOSE tip angles, not another root of the same base angles.
+    Configurations that sit on a fold of the base-angle map (singular Jacobian at the root: the robot is about to
+    snap) are excluded by the conditioning of the oracle's own finite-difference Jacobian."""
+    d = robots[name]
+    B = 300
+    T = d.ntubes
+    idx = util.alpha_indices(d)
+    jv = ctrfk.sample_joints_host(d, 78, 0, B)
+    rng = np.random.default_rng(5)
+    o = oracle.fk_batch(d, jv, ctrfk.MODE_NSAMPLE, nsamples=128)
+    jvb = util.base_angle_inputs(d, jv, o["alpha_base"])
+    guess = jv.copy()
+    guess[:, idx[1:]] += rng.uniform(-0.02, 0.02, size=(B, T - 1))
+    jt, it, st, res = _hostsim_shoot(hostsim, d, jvb, ctrfk.MODE_NSAMPLE, guess=guess, nsamples=128)
+    # conditioning of d base / d tip at the true root (central differences of the oracle)
+    eps = 1e-6
+    smin = np.zeros(B)
+    J = np.zeros((B, T - 1, T - 1))
+    for c in range(T - 1):
+        qp = jv.copy(); qm = jv.copy()
+        qp[:, idx[c + 1]] += eps; qm[:, idx[c + 1]] -= eps
+        J[:, :, c] = (oracle.fk_batch(d, qp, ctrfk.MODE_NSAMPLE, nsamples=128)["alpha_base"][:, 1:]
+                      - oracle.fk_batch(d, qm, ctrfk.MODE_NSAMPLE, nsamples=128)["alpha_base"][:, 1:]) / (2 * eps)
+    smin = np.linalg.svd(J, compute_uv=False)[:, -1]
+    regular = smin > 0.05                               # a 0.02 rad guess error stays inside Newton's basin
+    assert regular.mean() > 0.5
+    assert (st[regular] == 0).mean() >= 0.99, np.unique(st[regular], return_counts=True)
+    good = regular & (st == 0)
+    err = np.abs(jt[good][:, idx[1:]] - jv[good][:, idx[1:]]).max(axis=1)
+    assert (err < 1e-8).mean() >= 0.99, np.sort(err)[-5:]
+    assert it[good].mean() < 5.0                        # 3-4 sweeps from a nearby guess
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_rk4_sweep_matches_python_checker(ctrfk, hostsim, robots, name):
+    """CTR_FK_FLAG_RK4's sweep and its variational Jacobian (CPU build of the device code) against
+    oracle/ctr_shoot_rk4_py.py: same equations, written independently, derivative by complex step."""
+    import ctypes as C
+    import ctr_oracle_py as py
+    import ctr_shoot_rk4_py as rk
+    d = robots[name]
+    model = py.model_from_desc(d)
+    T = d.ntubes
+    jv = ctrfk.sample_joints_host(d, 31, 0, 6)
+    for q in jv:
+        for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=48)), (ctrfk.MODE_STEP, dict(step=d.max_length / 40.0))):
+            base = np.zeros(T); jac = np.zeros((T - 1, T - 1))
+            rc = hostsim.hostsim_tangent(C.addressof(d), q.ctypes.data, mode, kw.get("step", 0.0), kw.get("nsamples", 0), 1,
+                                         base.ctypes.data, jac.ctypes.data)
+            assert rc == 0
+            b, J = rk.base_angles_and_jacobian(model, q, mode, **kw)
+            assert np.abs(base - b).max() < 1e-11, (base, b)
+            assert np.abs(jac - J).max() < 1e-9 * max(1.0, np.abs(J).max()), (jac, J)
+
+
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_rk4_sweep_converges_to_the_reference_sweep(ctrfk, oracle, hostsim, robots, name):
+    """What ties the RK4 option to the reference: both integrate the same rod equations over the same arc interval
+    [h, ArcEnd], the reference by explicit Euler.  Their base angles differ by O(h): the gap halves when the sample
+    count doubles (medians over the configurations: these robots are close to snapping for many inputs, where the
+    base angles are very sensitive, so the maximum is dominated by a few of them)."""
+    import ctypes as C
+    d = robots[name]
+    T = d.ntubes
+    idx = util.alpha_indices(d)
+    jv = ctrfk.sample_joints_host(d, 32, 0, 120)
+    jv[:, idx[0]] = 0.0                                  # the RK4 model measures every angle from tube 0
+    d2 = ctrfk.RobotDesc.from_buffer_copy(d)
+    d2.max_samples = 4096
+
+    def rk4(n):
+        out = np.zeros((jv.shape[0], T))
+        for i, q in enumerate(jv):
+            jac = np.zeros((T - 1, T - 1))
+            assert hostsim.hostsim_tangent(C.addressof(d2), q.ctypes.data, ctrfk.MODE_NSAMPLE, 0.0, n, 1,
+                                           out[i].ctypes.data, jac.ctypes.data) == 0
+        return out
+
+    gaps = []
+    for n in (128, 256, 512, 1024):
+        e = oracle.fk_batch(d2, jv, ctrfk.MODE_NSAMPLE, nsamples=n)["alpha_base"]
+        gaps.append(np.median(np.abs(e - rk4(n)).max(axis=1)))
+    for a, b in zip(gaps, gaps[1:]):
+        assert 1.5 < a / b < 3.0, gaps                  # first order: Euler's error, not RK4's
+
+
+@pytest.mark.parametrize("name", ["ctr_sec2_tub3.xml", "ctr_sec3_tub5.xml"])
+def test_rk4_sweep_is_fourth_order(ctrfk, hostsim, robots, name):
+    """The RK4 sweep's own error, measured against the same arc interval integrated with every step cut into 16
+    parts (Python checker): fourth order — because a step is split where a section's curved interval starts or ends;
+    stepping across those jumps leaves a first-order error as large as Euler's (checker with split=False)."""
+    import ctypes as C
+    import ctr_oracle_py as py
+    import ctr_shoot_rk4_py as rk
+    d = robots[name]
+    model = py.model_from_desc(d)
+    T = d.ntubes
+    idx = util.alpha_indices(d)
+    jv = ctrfk.sample_joints_host(d, 33, 0, 10)
+    jv[:, idx[0]] = 0.0
+    err = {32: [], 64: []}
+    nosplit = []
+    for q in jv:
+        for n in (32, 64):
+            base = np.zeros(T); jac = np.zeros((T - 1, T - 1))
+            assert hostsim.hostsim_tangent(C.addressof(d), q.ctypes.data, ctrfk.MODE_NSAMPLE, 0.0, n, 1,
+                                           base.ctypes.data, jac.ctypes.data) == 0
+            fine = np.real(rk.base_angles(model, q.astype(complex), ctrfk.MODE_NSAMPLE, nsamples=n, refine=16)[0])
+            err[n].append(np.abs(base - fine).max())
+            if n == 64:
+                ns = np.real(rk.base_angles(model, q.astype(complex), ctrfk.MODE_NSAMPLE, nsamples=n, split=False)[0])
+                nosplit.append(np.abs(ns - fine).max())
+    assert max(err[64]) < 2e-5 and np.median(err[64]) < 1e-7, (err[64])
+    assert np.median(err[32]) / np.median(err[64]) > 10.0            # 2^4 = 16 in the limit
+    assert np.median(nosplit) > 1e4 * np.median(err[64])
+
+
+@pytest.mark.parametrize("name", ["ctr_sec2_tub3.xml", "ctr_sec3_tub4.xml"])
+def test_rk4_shooting_roots_approach_the_reference_roots(ctrfk, oracle, hostsim, robots, name):
+    """CTR_FK_FLAG_RK4 end to end on the CPU build: (a) its roots are roots of the Python checker's RK4 sweep;
+    (b) started from the reference-exact tip angles they stay on that branch and differ from them by O(h)."""
+    import ctr_oracle_py as py
+    import ctr_shoot_rk4_py as rk
+    d = robots[name]
+    idx = util.alpha_indices(d)
+    model = py.model_from_desc(d)
+    jv = ctrfk.sample_joints_host(d, 79, 0, 150)
+    jv[:, idx[0]] = 0.0
+    dist = []
+    for n in (64, 128, 256):
+        o = oracle.fk_batch(d, jv, ctrfk.MODE_NSAMPLE, nsamples=n)
+        jvb = util.base_angle_inputs(d, jv, o["alpha_base"])
+        jt, it, st, res = _hostsim_shoot(hostsim, d, jvb, ctrfk.MODE_NSAMPLE, guess=jv, nsamples=n, rk4=1)
+        ok = st == 0
+        assert ok.mean() > 0.7                          # the rest sits near a fold: no RK4 root on the reference's branch
+        if n == 64:
+            for i in np.flatnonzero(ok)[:8]:
+                b, _, _ = rk.base_angles(model, jt[i].astype(complex), ctrfk.MODE_NSAMPLE, nsamples=n)
+                assert np.abs(np.real(b[1:]) - jvb[i, idx[1:]]).max() < 1e-10
+        dist.append(np.abs(jt[:, idx[1:]] - jv[:, idx[1:]]).max(axis=1))
+    both = (dist[0] < 0.2) & (dist[1] < 0.2) & (dist[2] < 0.2)          # same branch at every resolution
+    assert both.mean() > 0.6
+    m = [np.median(x[both]) for x in dist]
+    assert m[0] > m[1] > m[2] and 2.5 < m[0] / m[2] < 6.0, m          # O(h): a factor 4 from N = 64 to N = 256
 
 
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
@@ -164,8 +322,6 @@ def test_tangent_sweep_jacobian(ctrfk, oracle, hostsim, robots, name):
     """The variational Jacobian d(base angles)/d(tip angles) of the shooting solve against central
     differences of the ORACLE's base angles, and its base angles against the oracle's."""
     import ctypes as C
-    hostsim.hostsim_tangent.restype = C.c_int
-    hostsim.hostsim_tangent.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     d = robots[name]
     T = d.ntubes
     idx = util.alpha_indices(d)
@@ -173,7 +329,7 @@ def test_tangent_sweep_jacobian(ctrfk, oracle, hostsim, robots, name):
     for q in jv:
         for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=96)), (ctrfk.MODE_STEP, dict(step=d.max_length / 80.0))):
             base = np.zeros(T); jac = np.zeros((T - 1, T - 1))
-            rc = hostsim.hostsim_tangent(C.addressof(d), q.ctypes.data, mode, kw.get("step", 0.0), kw.get("nsamples", 0),
+            rc = hostsim.hostsim_tangent(C.addressof(d), q.ctypes.data, mode, kw.get("step", 0.0), kw.get("nsamples", 0), 0,
                                          base.ctypes.data, jac.ctypes.data)
             assert rc == 0
             o = oracle.fk_one(d, q, mode, **kw)

@@ -33,8 +33,10 @@ def load_hostsim():
     lib.hostsim_sincos.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.hostsim_se3.argtypes = [C.c_double] * 4 + [C.c_void_p] * 2
     lib.hostsim_shoot.restype = C.c_int
-    lib.hostsim_shoot.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
-                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hostsim_shoot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double,
+                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hostsim_tangent.restype = C.c_int
+    lib.hostsim_tangent.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
