@@ -71,11 +71,13 @@ extern "C" {
 #define CTR_FK_E_ARG       -3   /* invalid argument (mode, step<=0, nsamples<1, B<0 ...)         */
 #define CTR_FK_E_XML       -4   /* XML file unreadable or malformed                             */
 #define CTR_FK_E_NOMEM     -5   /* host allocation failed                                       */
+#define CTR_FK_E_RANGE     -6   /* ctr_fk_single only: some Phi outside [0, Length]; outputs NaN */
 
 /* per-configuration status bits written to the optional `status` output */
 #define CTR_FK_STATUS_OK        0
 #define CTR_FK_STATUS_PHI_RANGE 1   /* some Phi outside [0, Length] (reference: assert, section_i.h:205);
-                                       outputs for that configuration are NaN                 */
+                                       that configuration's tip, step_out, alpha_base, frame 0 of its
+                                       backbone row and radius 0 are NaN, its n_out is 0      */
 
 /* One section = 1 tube (CC) or 2 tubes (VC), section_i.h:365-369. */
 typedef struct ctr_section_desc {
@@ -164,6 +166,9 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
  * Only tip / n_out / step_out / status are offered here (backbone output is 26 KB per configuration
  * and is meant to stay on the device; see ctr_fk_batch_host_backbone). */
 #define CTR_FK_FLAG_HOST_STAGED 0x800u
+/* ctr_fk_batch_host only: the FP32 state arithmetic of ctr_fk_batch_f32 (chunked copy pipeline; doubles at the
+ * interface) — what ctrb200::RobotF, the shape of the reference's CTR::Robot<float>, calls */
+#define CTR_FK_FLAG_F32         0x2000u
 int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                       int32_t nsamples, uint32_t flags,
                       double* tip, int32_t* n_out, double* step_out, int32_t* status);
@@ -179,8 +184,10 @@ int ctr_fk_host_alloc(ctr_fk_handle h, size_t bytes, uint32_t flags, void** ptr)
 int ctr_fk_host_free(ctr_fk_handle h, void* ptr);
 int ctr_fk_host_local_cpus(ctr_fk_handle h, char* buf, size_t len);
 
-/* HOST pointers, WITH the backbone: backbone [B][max_samples][12] (required; the first n_out[i] frames of row i are
- * written, getTransformSample of robot_i.h:527), radius [B][max_samples] (nullable, getRadiusSample :526), the rest
+/* HOST pointers, WITH the backbone: backbone [B][max_samples][12] (required; whole rows are copied back: the first
+ * n_out[i] frames of row i are getTransformSample of robot_i.h:527, the entries behind them are unspecified scratch,
+ * and a configuration with status != 0 has n_out 0 and NaN in frame 0), radius [B][max_samples] (nullable,
+ * getRadiusSample :526; same rule), the rest
  * as ctr_fk_batch_host.  104 * max_samples bytes per configuration come back over PCIe, which bounds this call. */
 int ctr_fk_batch_host_backbone(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step,
                                int32_t nsamples, uint32_t flags, double* tip, double* backbone,
@@ -216,7 +223,9 @@ int ctr_fk_peer_free(ctr_fk_handle h, void* dptr);
 /* One configuration, HOST pointers, synchronous: the reference's single-shot call
  * (robot_i.h:690-755) served by the same kernels with B = 1.  The handle keeps a small device
  * scratch for it; calls on one handle are serialised.  backbone [max_samples][12], radius
- * [max_samples]; every output nullable. */
+ * [max_samples]; every output nullable.  Returns CTR_FK_E_RANGE (outputs NaN, *n_out = 0) when the
+ * configuration's status is CTR_FK_STATUS_PHI_RANGE — a code of its own, so that it cannot be taken for
+ * cudaError_t 1. */
 int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int32_t nsamples,
                   uint32_t flags, double* tip, double* backbone, double* radius, int32_t* n_out,
                   double* step_out, double* alpha_base);

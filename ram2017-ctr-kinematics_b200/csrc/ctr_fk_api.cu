@@ -38,6 +38,10 @@ struct ctr_fk_engine {
     char*          single_buf;   // device scratch of ctr_fk_single (lazily allocated)
     char*          stage_buf;    // device staging slabs of ctr_fk_batch_host (grow-only, cached)
     size_t         stage_bytes;
+    cudaMemPool_t  pool;         // private pool of the stream-ordered temporaries (binning order, tickets, staging
+                                 // slabs of the host-pointer calls): freed blocks stay here for the next call and go
+                                 // back to the driver with the handle, never parked in the device's default pool
+                                 // that the caller's own allocator (torch, ...) shares
 };
 
 namespace {
@@ -106,7 +110,7 @@ cudaError_t make_order(ctr_fk_handle h, const double* jv, int64_t B, int mode, d
                        int32_t** order_out, cudaStream_t st)
 {
     int32_t* order = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&order, sizeof(int32_t) * (size_t)B, st);
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&order, sizeof(int32_t) * (size_t)B, h->pool, st);
     if (e != cudaSuccess) return e;
     e = launch_bin_local(h->key, h->rb, jv, B, mode, step, ns, order, st);
     if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
@@ -179,19 +183,22 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
         set_error("ctr_fk_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
         return (int)cudaErrorNoKernelImageForDevice;
     }
-    {   // step mode and the shooting solve take stream-ordered temporaries; keep freed blocks in the
-        // device's default pool instead of returning them to the driver at every synchronisation
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        (void)cudaGetLastError();
-    }
     ctr_fk_engine* h = new (std::nothrow) ctr_fk_engine;
     if (!h) { set_error("out of host memory"); return CTR_FK_E_NOMEM; }
     h->desc = *desc;
     h->rb = rb;
+    h->pool = nullptr;
+    {
+        cudaMemPoolProps pp = {};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        cudaError_t pe = cudaMemPoolCreate(&h->pool, &pp);
+        if (pe != cudaSuccess) { delete h; return cuda_fail("ctr_fk_create: cudaMemPoolCreate", pe); }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     h->key = layout_key(desc);
     h->device = device;
     h->ntubes = desc_ntubes(desc);
@@ -227,6 +234,7 @@ int ctr_fk_destroy(ctr_fk_handle h)
             if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
         if (h->single_buf) cudaFree(h->single_buf);
         if (h->stage_buf) cudaFree(h->stage_buf);
+        if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
     }
     delete h;
     return 0;
@@ -362,7 +370,7 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     // 96-byte rows would cross PCIe as scattered 16-byte writes (and the binning pass would read the joint vectors
     // over PCIe a second time).
     const bool binned = mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples;
-    if (h->host_zero_copy && !binned && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED)) && tip && aligned16(jv) && aligned16(tip)) {
+    if (h->host_zero_copy && !binned && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED | CTR_FK_FLAG_F32)) && tip && aligned16(jv) && aligned16(tip)) {
         const size_t nb = (size_t)B;
         double*  z_jv   = (double*)device_alias(jv, sizeof(double) * nb * h->njv);
         double*  z_tip  = (double*)device_alias(tip, sizeof(double) * nb * 12);
@@ -422,7 +430,9 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
         int32_t* d_stat = status ? (int32_t*)(base + off_stat) : nullptr;
         // stream order protects slab reuse: chunk c and chunk c+nslab share a stream
         if ((e = cudaMemcpyAsync(d_jv, jv + done * njv, sizeof(double) * (size_t)nb * njv, cudaMemcpyHostToDevice, st)) != cudaSuccess) { ret = cuda_fail("H2D copy", e); break; }
-        ret = run_batch(h, d_jv, nb, mode, step, nsamples, flags, d_tip, nullptr, nullptr, d_n, d_step, nullptr, d_stat, st);
+        ret = (flags & CTR_FK_FLAG_F32)
+                  ? ctr_fk_batch_f32(h, d_jv, nb, mode, step, nsamples, flags & ~(uint32_t)(CTR_FK_FLAG_F32 | CTR_FK_FLAG_HOST_STAGED), d_tip, d_n, d_step, d_stat, st)
+                  : run_batch(h, d_jv, nb, mode, step, nsamples, flags, d_tip, nullptr, nullptr, d_n, d_step, nullptr, d_stat, st);
         if (ret) break;
         if (tip && (e = cudaMemcpyAsync(tip + done * 12, d_tip, sizeof(double) * (size_t)nb * 12, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
         if (n_out && (e = cudaMemcpyAsync(n_out + done, d_n, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { ret = cuda_fail("D2H copy", e); break; }
@@ -472,7 +482,7 @@ int ctr_fk_batch_host_backbone(ctr_fk_handle h, const double* jv, int64_t B, int
     const int nslab = (int)std::min<int64_t>(NS, (B + chunk - 1) / chunk);
 
     char* dbuf = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&dbuf, slab * (size_t)nslab, h->streams[0]);
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&dbuf, slab * (size_t)nslab, h->pool, h->streams[0]);
     if (e != cudaSuccess) return cuda_fail("ctr_fk_batch_host_backbone: device staging allocation", e);
     if ((e = cudaStreamSynchronize(h->streams[0])) != cudaSuccess) { cudaFreeAsync(dbuf, h->streams[0]); return cuda_fail("ctr_fk_batch_host_backbone: sync", e); }
 
@@ -635,7 +645,7 @@ int ctr_fk_single(ctr_fk_handle h, const double* jv, int mode, double step, int3
         if (radius && (e = cudaMemcpy(radius, d + o_rad, sizeof(double) * (size_t)nn[0], cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail("D2H copy", e);
         if (backbone && (e = cudaMemcpy(backbone, d + o_bb, sizeof(double) * 12 * (size_t)nn[0], cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail("D2H copy", e);
     }
-    return nn[1] ? CTR_FK_STATUS_PHI_RANGE : 0;
+    return nn[1] ? CTR_FK_E_RANGE : 0;
 }
 
 int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, double step, int32_t nsamples,
@@ -737,7 +747,7 @@ int ctr_fk_jacobian_host_ex(ctr_fk_handle h, const double* jv, int64_t B, int mo
     // synchronisation per call, which matters for the one-configuration calls of ctrb200::Robot
     char* d = nullptr;
     cudaStream_t st = h->streams[0];
-    cudaError_t e = cudaMallocAsync((void**)&d, b_jv + 2 * b_jac + 2 * b_tip + b_n, st);
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&d, b_jv + 2 * b_jac + 2 * b_tip + b_n, h->pool, st);
     if (e != cudaSuccess) return cuda_fail("ctr_fk_jacobian_host: allocation", e);
     double*  d_jv   = (double*)d;
     double*  d_jac  = (double*)(d + b_jv);
@@ -809,7 +819,7 @@ int ctr_fk_stability_batch_ex(ctr_fk_handle h, const double* jv, int64_t B, doub
     a.stable = stable; a.degree = degree;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* ticket = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&ticket, sizeof(unsigned long long), st);
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&ticket, sizeof(unsigned long long), h->pool, st);
     if (e != cudaSuccess) return cuda_fail("ticket allocation", e);
     e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     a.ticket = ticket;
@@ -840,7 +850,7 @@ int ctr_fk_stability_host_ex(ctr_fk_handle h, const double* jv, int64_t B, doubl
     const size_t b_jv = up256(n_jv), b_deg = up256(sizeof(double) * (size_t)B), b_st = sizeof(int32_t) * (size_t)B;
     char* d = nullptr;
     cudaStream_t st = h->streams[0];
-    cudaError_t e = cudaMallocAsync((void**)&d, b_jv + b_deg + b_st, st);
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&d, b_jv + b_deg + b_st, h->pool, st);
     if (e != cudaSuccess) return cuda_fail("ctr_fk_stability_host: allocation", e);
     double* d_jv = (double*)d;
     double* d_deg = (double*)(d + b_jv);
@@ -885,7 +895,7 @@ int ctr_fk_batch_base_ex(ctr_fk_handle h, const double* jv_base, const double* j
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* ticket = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&ticket, sizeof(unsigned long long), st);
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&ticket, sizeof(unsigned long long), h->pool, st);
     if (e != cudaSuccess) return cuda_fail("ticket allocation", e);
     e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
     int32_t* order = nullptr;

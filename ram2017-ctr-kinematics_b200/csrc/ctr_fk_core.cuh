@@ -111,6 +111,17 @@ CTR_HD double x_fma(double a, double b, double c)
 #endif
 }
 
+// An empty asm that "modifies" x: the value becomes opaque to the optimiser, which can then neither fold it nor
+// rematerialise it later from its operands.
+CTR_HD void keep_in_register(double& x)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(x));
+#else
+    (void)x;
+#endif
+}
+
 // Control block of one configuration.
 template <class L>
 struct Ctl {
@@ -375,6 +386,8 @@ struct FastConsts {
     double c[6];      // cos kernel
     double qa4[4], qb4[4], qc4[4];   // SE(3) series for m <= 2^-8, Horner order
     double qa8[7], qb8[7], qc8[7];   // SE(3) series for m <= 2^-4
+    // run_scaled: 4 (|phi| - sin|phi|) / |phi|^3 - 2/3 as a series in m = (|phi|/2)^2, Horner order
+    double qcs4[2];
 };
 
 #define CTRK_FAST_CONSTS_INIT                                                                      \
@@ -393,7 +406,8 @@ struct FastConsts {
             {-1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0,        \
              -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0},                                              \
             {4096.0 / 1307674368000.0, -1024.0 / 6227020800.0, 256.0 / 39916800.0,                 \
-             -64.0 / 362880.0, 16.0 / 5040.0, -4.0 / 120.0, 1.0 / 6.0}                             \
+             -64.0 / 362880.0, 16.0 / 5040.0, -4.0 / 120.0, 1.0 / 6.0},                            \
+            {64.0 / 5040.0, -16.0 / 120.0}                                                         \
     }
 // NB: qc8's last entry is the constant term 1/6 (its Horner chain has no separate "+1" step).
 
@@ -651,7 +665,7 @@ CTR_HD void se3_step_fast(double ux, double uy, double uz, double h, double ztol
 // ztol <= |u| and (h|u|/2)^2 < 2^-8; all benchmark workloads are 100 % hot.  Anything else (coarse
 // sampling, zero curvature) takes the generic iteration.
 #ifdef CTRK_COUNT_COLD
-static long long g_iter_total = 0, g_iter_cold = 0, g_iter_cold_delta = 0;
+static long long g_iter_total = 0, g_iter_cold = 0, g_iter_cold_delta = 0, g_iter_block = 0, g_iter_blockhot = 0;
 #endif
 // Carried sin/cos are rotated by the step increment d with the degree-8/9 Taylor pair while
 // |d| < 0.09375 (high word of 1.5 * 2^-4): truncation d^10/10! < 1.5e-17, d^11/11! < 2e-19.
@@ -899,6 +913,247 @@ struct FastSweep {
         if (!TAIL) pos = x_sub(pos, c.h);
     }
 
+    // top-of-iteration quantities shared by the tier tests and the hot steps; returns the tier (0: hot + rotate,
+    // 1: hot + sincos_bounded, 2: generic) — what run() computes inline, for callers that step two sweeps in lock-step
+    CTR_HD int classify(double* dl, double& sxy, double& m) const
+    {
+        int dmax = 0, amax = 0;
+        const double z0 = uzs[0];
+#pragma unroll
+        for (int t = 1; t < T; ++t) {
+            dl[t] = c.h * (uzs[t] - z0);
+            const int d = hi_word(dl[t]) & 0x7fffffff;
+            const int a = hi_word(al[t]) & 0x7fffffff;
+            dmax = d > dmax ? d : dmax;
+            amax = a > amax ? a : amax;
+        }
+        sxy = x_fma(puy, puy, pux * pux);
+        const double n2 = x_fma(puz, puz, sxy);
+        m = n2 * kc.hh2;
+        const bool se3_hot = !want_tip || (le_nonneg(kc.ztol2, n2) && hi_word(m) < 0x3f700000);
+        if (se3_hot && dmax < kRotMaxHi) return 0;
+        if (se3_hot && amax < 0x408f0000 && dmax < 0x40300000) return 1;
+        return 2;
+    }
+    CTR_HD void step_tier(int tier, int k, const double* dl, double sxy, double m)
+    {
+        if (tier == 0)      step<false, false, true, true>(k, dl, sxy, m);
+        else if (tier == 1) step<false, false, true, false>(k, dl, sxy, m);
+        else                step<false, false, false>(k, dl, sxy, m);
+    }
+
+    // ---- run_scaled(): the sweep of run() with the state in units of the step ------------------------------------
+    // A good part of run()'s hot iteration is not arithmetic of the recurrence but the factors h, h/2, (h/2)^2, h^3
+    // that turn (u, z) into the step's half rotation vector psi = (h/2) u.  Here the loop keeps the state in those
+    // units: w_t = h z_t, curvature weights (h/2) kgr (so x_t, y come out as components of psi), translation P / h.
+    // Then d_t = w_t - w_0, the series run in m = |psi|^2 with the tables of run(), the step's quaternion is
+    // (qa, qb psi) and its translation needs no h: 8 FP64 instructions fewer per step (113 -> 105 on the 3-tube
+    // robot), and the tier test needs no |alpha| reduction (only the middle tier evaluates sin/cos of an angle).  An
+    // iteration that is not hot converts the state back, runs run()'s own iteration and converts again (rare: coarse
+    // sampling, zero curvature); everything only that path needs (1/h, the step constants, h (1+nu) kappa) is
+    // recomputed there, so it does not occupy registers in the hot loop.  The sweep itself needs only sin/cos of the
+    // tube angles: a generic iteration gets the angles modulo 2 pi from the carried pair, and the angles themselves
+    // are accumulated only with KEEP_AL (when they are an output).  Same arithmetic per step as run() up to the
+    // placement of the factor h (FAST: results agree to rounding).
+    static constexpr int NG = S * (S + 1) / 2;
+#ifndef CTRK_SCALED_UNROLL
+#define CTRK_SCALED_UNROLL 2
+#endif
+    // two iterations per trip: the copies that hand the loop-carried state from one iteration to the next and half
+    // of the loop control disappear (tools/tune_tip.cu: 1.89 -> 1.85 ms per 1M on the 3-tube robot, 2.86 -> 2.72 on
+    // the 5-tube one)
+    static constexpr int kScaledUnroll = CTRK_SCALED_UNROLL;
+
+    // one hot iteration; dl[t] = w_t - w_0, (sxy, m) = |psi_xy|^2, |psi|^2 of the pending sample (pux, puy, puz = psi)
+    template <bool KEEP_AL>
+    CTR_HD void hot_scaled_step(const double* hg, const double* hko2, double* w, const double* dl, double sxy, double m)
+    {
+        // ---- (A) accumulate the pending sample -------------------------------------------------------------------
+        if (want_tip) {
+            double qa = x_fma(CTRK_FC.qa4[0], m, CTRK_FC.qa4[1]);
+            double qb = x_fma(CTRK_FC.qb4[0], m, CTRK_FC.qb4[1]);
+            double qc = x_fma(CTRK_FC.qcs4[0], m, CTRK_FC.qcs4[1]);
+            qa = x_fma(qa, m, CTRK_FC.qa4[2]);
+            qb = x_fma(qb, m, CTRK_FC.qb4[2]);
+            qc = x_fma(qc, m, 2.0 / 3.0);                 // 4 (|phi| - sin|phi|) / |phi|^3
+            qa = x_fma(qa, m, CTRK_FC.qa4[3]);
+            qb = x_fma(qb, m, CTRK_FC.qb4[3]);
+            qa = x_fma(qa, m, 1.0);                       // cos(|phi|/2)
+            qb = x_fma(qb, m, 1.0);                       // sin(|phi|/2) / (|phi|/2)
+            const double ex = qb * pux, ey = qb * puy, ez = qb * puz;
+            const double cz = qc * puz;
+            apply(qa, ex, ey, ez, x_fma(cz, pux, qb * ey), x_fma(cz, puy, -(qb * ex)), x_fma(-qc, sxy, 1.0));
+        }
+        // ---- (B) this sample ------------------------------------------------------------------------------------
+        bool in_k[S], in_c[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            in_k[s] = (s == S - 1) ? true : le_nonneg(pos, c.end[s]);
+            in_c[s] = in_k[s] && le_nonneg(c.start[s], pos);
+        }
+        double cx = 0.0, cy = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            double gr = hg[s * (s + 1) / 2 + s];
+#pragma unroll
+            for (int p2 = s - 1; p2 >= 0; --p2) gr = in_k[p2] ? hg[s * (s + 1) / 2 + p2] : gr;
+            const double g = in_c[s] ? gr : 0.0;
+#pragma unroll
+            for (int j = 0; j < L::nt(s); ++j) {
+                const int t = L::t0(s) + j;
+                if (t == 0) { cy = g; first = false; continue; }            // tube 0: sin 0 = 0, cos 0 = 1
+                if (first) { cx = -sn[t] * g; cy = cs[t] * g; first = false; }
+                else       { cx = x_fma(-sn[t], g, cx); cy = x_fma(cs[t], g, cy); }
+            }
+        }
+        double uxs[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) uxs[t] = (t == 0) ? cx : x_fma(cs[t], cx, sn[t] * cy);
+        const double uy_in = (T == 1) ? cy : x_fma(cs[T - 1], cy, -(sn[T - 1] * cx));
+        const double pz_k = 0.5 * w[T - 1];
+        if (KEEP_AL) {
+#pragma unroll
+            for (int t = 1; t < T; ++t) al[t] = al[t] + dl[t];
+        }
+        if (T > 1) {
+            double zl = 0.0;
+#pragma unroll
+            for (int t = T - 2; t >= 0; --t) {
+                const double hk = in_c[L::sec_of(t)] ? hko2[t] : 0.0;
+                zl   = (t == T - 2) ? rb.nczc[t] * w[t] : x_fma(rb.nczc[t], w[t], zl);
+                w[t] = x_fma(hk, uxs[t], w[t]);
+            }
+            w[T - 1] = zl;
+        } else {
+            w[0] = 0.0;
+        }
+#pragma unroll
+        for (int t = 1; t < T; ++t) {
+            const double d  = dl[t];
+            const double d2 = d * d;
+            double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
+            double ps = x_fma(CTRK_FC.qb4[0], d2, CTRK_FC.qb4[1]);
+            pc = x_fma(pc, d2, CTRK_FC.qa4[2]);
+            ps = x_fma(ps, d2, CTRK_FC.qb4[2]);
+            pc = x_fma(pc, d2, CTRK_FC.qa4[3]);
+            ps = x_fma(ps, d2, CTRK_FC.qb4[3]);
+            const double cd = x_fma(pc, d2, 1.0);
+            const double sd = x_fma(d * d2, ps, d);
+            const double s1 = x_fma(cs[t], sd, sn[t] * cd);
+            const double c1 = x_fma(-sn[t], sd, cs[t] * cd);
+            sn[t] = s1; cs[t] = c1;
+        }
+        pux = uxs[T - 1]; puy = uy_in; puz = pz_k;
+        pos = x_sub(pos, c.h);
+    }
+
+    template <bool KEEP_AL>
+    CTR_HD void run_scaled()
+    {
+        const int n = c.n;
+        if (n < 8 || !(c.h > 1e-150)) { run(); return; }      // short sweeps; a retracted robot (h = 0) has no 1 / h
+        double dl[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) dl[t] = 0.0;
+        step<true, false, false>(n - 1, dl, 0.0, 0.0);
+        {   // the iteration that can hold the tip sample of a step-mode sweep (k == nframes - 1) stays generic
+            double sxy, m;
+            const int tier = classify(dl, sxy, m);
+            step_tier(tier, n - 2, dl, sxy, m);
+        }
+        const double h = c.h, hh = 0.5 * c.h;
+        double hg[NG], hko2[T > 1 ? T - 1 : 1];
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2)
+#pragma unroll
+            for (int q = 0; q <= s2; ++q) hg[s2 * (s2 + 1) / 2 + q] = hh * rb.kgr[s2][q];
+#pragma unroll
+        for (int t = 0; t + 1 < T; ++t) hko2[t] = 2.0 * hko[t];
+        double zt2s = (rb.ztol * rb.ztol) * (hh * hh);
+        // loop invariants the compiler would otherwise recompute in every iteration (it prefers 13 FP64 instructions
+        // per step to 7 live register pairs): made opaque, so they stay in registers
+#pragma unroll
+        for (int i = 0; i < NG; ++i) keep_in_register(hg[i]);
+#pragma unroll
+        for (int t = 0; t + 1 < T; ++t) keep_in_register(hko2[t]);
+        keep_in_register(zt2s);
+        // into units of the step
+        double w[T];
+        {
+            const double inv_h = 1.0 / h;
+#pragma unroll
+            for (int t = 0; t < T; ++t) w[t] = h * uzs[t];
+            pux *= hh; puy *= hh; puz *= hh;
+            Px *= inv_h; Py *= inv_h; Pz *= inv_h;
+        }
+        // |psi|^2 = m is hot when zt2s < m < 2^-8; on the high words: hi(zt2s) < hi(m) < hi(2^-8), one unsigned range
+        // compare (a tie of the high words goes to the generic iteration, which compares exactly)
+        const unsigned m_lo = (unsigned)hi_word(zt2s) + 1u, m_span = 0x3f700000u - m_lo;
+#pragma unroll kScaledUnroll
+        for (int k = n - 3; k >= 1; --k) {
+            int dmax = 0;
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                dl[t] = w[t] - w[0];
+                const int d = hi_word(dl[t]) & 0x7fffffff;
+                dmax = d > dmax ? d : dmax;
+            }
+            const double sxy = x_fma(puy, puy, pux * pux);
+            const double m   = x_fma(puz, puz, sxy);
+            // hot: every |d_t| < 0.09375, zero tolerance <= |u|, (h|u|/2)^2 < 2^-8
+            const bool hot = dmax < kRotMaxHi && (!want_tip || ((unsigned)hi_word(m) - m_lo) < m_span);
+#ifdef CTRK_COUNT_COLD   /* host-side analysis builds only (tests/hostsim) */
+            ++g_iter_block; if (hot) ++g_iter_blockhot;
+#endif
+            if (hot) {
+                hot_scaled_step<KEEP_AL>(hg, hko2, w, dl, sxy, m);
+            } else {
+                // back to (u, z, P), one iteration of run(), and into units of the step again.  The generic
+                // iteration evaluates sin/cos of the tube angles; it gets them modulo 2 pi from the carried pair in
+                // BOTH forms of this loop, so the pose does not depend on whether the angles are an output too.
+                const double inv_h = 1.0 / h, inv_hh = 2.0 * inv_h;
+                kc = make_step_consts(h, rb.ztol);
+#pragma unroll
+                for (int t = 0; t + 1 < T; ++t) hko[t] = 0.5 * hko2[t];
+#pragma unroll
+                for (int t = 0; t < T; ++t) uzs[t] = w[t] * inv_h;
+                pux *= inv_hh; puy *= inv_hh; puz *= inv_hh;
+                Px *= h; Py *= h; Pz *= h;
+                double al_out[T];
+#pragma unroll
+                for (int t = 1; t < T; ++t) { al_out[t] = al[t]; al[t] = atan2(sn[t], cs[t]); }
+                double sxy_u, m_u;
+                const int tier = classify(dl, sxy_u, m_u);
+                step_tier(tier, k, dl, sxy_u, m_u);
+                if (KEEP_AL) {
+#pragma unroll
+                    for (int t = 1; t < T; ++t) al[t] = al_out[t] + dl[t];
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t) w[t] = h * uzs[t];
+                pux *= hh; puy *= hh; puz *= hh;
+                Px *= inv_h; Py *= inv_h; Pz *= inv_h;
+            }
+        }
+        {
+            const double inv_h = 1.0 / h, inv_hh = 2.0 * inv_h;
+            kc = make_step_consts(h, rb.ztol);
+#pragma unroll
+            for (int t = 0; t + 1 < T; ++t) hko[t] = 0.5 * hko2[t];
+#pragma unroll
+            for (int t = 0; t < T; ++t) uzs[t] = w[t] * inv_h;
+            pux *= inv_hh; puy *= inv_hh; puz *= inv_hh;
+            Px *= h; Py *= h; Pz *= h;
+        }
+        {
+            const double z0 = uzs[0];
+#pragma unroll
+            for (int t = 1; t < T; ++t) dl[t] = c.h * (uzs[t] - z0);    // unused by the tail
+        }
+        step<false, true, false>(0, dl, 0.0, 0.0);
+    }
+
     // Full sweep for a functor that emits frames one sample late (PendingFrameEmitter; thread-per-
     // configuration backbone kernel): as run(), with the frame of sample k+1 built inside
     // iteration k.  An iteration is hot when both the sweep and the pending frame qualify for
@@ -989,37 +1244,91 @@ struct FastSweep {
 };
 
 // WANT_TIP = false skips the frame product (sample-only sweeps: STRICT backbone kernel, stability).
+// quaternion -> rotation (normalised: |Q| drifts by ~N ulp), then Init * Rz * P
+template <class L, class Sweep>
+CTR_HD void finish_tip(const KRobot& rb, const Ctl<L>& c, const Sweep& sw, double* tip)
+{
+    const double Qw = sw.Qw, Qx = sw.Qx, Qy = sw.Qy, Qz = sw.Qz;
+    const double nn = Qw * Qw + Qx * Qx + Qy * Qy + Qz * Qz;
+    const double sc = 2.0 / nn;
+    double Pm[12];
+    Pm[0] = 1.0 - sc * (Qy * Qy + Qz * Qz);
+    Pm[1] = sc * (Qx * Qy + Qw * Qz);
+    Pm[2] = sc * (Qx * Qz - Qw * Qy);
+    Pm[3] = sc * (Qx * Qy - Qw * Qz);
+    Pm[4] = 1.0 - sc * (Qx * Qx + Qz * Qz);
+    Pm[5] = sc * (Qy * Qz + Qw * Qx);
+    Pm[6] = sc * (Qx * Qz + Qw * Qy);
+    Pm[7] = sc * (Qy * Qz - Qw * Qx);
+    Pm[8] = 1.0 - sc * (Qx * Qx + Qy * Qy);
+    Pm[9] = sw.Px; Pm[10] = sw.Py; Pm[11] = sw.Pz;
+    double sa, ca;
+    fast_sincos(sw.a_tip + c.theta, sa, ca);
+    tf_finish(rb.ini, Pm, sa, ca, tip);
+}
+
+// WANT_TIP = false skips the frame product (sample-only sweeps: STRICT backbone kernel, stability).
 template <class L, bool WANT_TIP, class OnSample>
 CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* albase,
                        OnSample on_sample)
 {
     constexpr int T = L::T;
     FastSweep<L, WANT_TIP, OnSample> sw(rb, c, on_sample);
-    sw.run();
-    if (WANT_TIP && tip) {
-        // quaternion -> rotation (normalised: |Q| drifts by ~N ulp), then Init * Rz * P
-        const double Qw = sw.Qw, Qx = sw.Qx, Qy = sw.Qy, Qz = sw.Qz;
-        const double nn = Qw * Qw + Qx * Qx + Qy * Qy + Qz * Qz;
-        const double sc = 2.0 / nn;
-        double Pm[12];
-        Pm[0] = 1.0 - sc * (Qy * Qy + Qz * Qz);
-        Pm[1] = sc * (Qx * Qy + Qw * Qz);
-        Pm[2] = sc * (Qx * Qz - Qw * Qy);
-        Pm[3] = sc * (Qx * Qy - Qw * Qz);
-        Pm[4] = 1.0 - sc * (Qx * Qx + Qz * Qz);
-        Pm[5] = sc * (Qy * Qz + Qw * Qx);
-        Pm[6] = sc * (Qx * Qz + Qw * Qy);
-        Pm[7] = sc * (Qy * Qz - Qw * Qx);
-        Pm[8] = 1.0 - sc * (Qx * Qx + Qy * Qy);
-        Pm[9] = sw.Px; Pm[10] = sw.Py; Pm[11] = sw.Pz;
-        double sa, ca;
-        fast_sincos(sw.a_tip + c.theta, sa, ca);
-        tf_finish(rb.ini, Pm, sa, ca, tip);
+    if (std::is_same<OnSample, NoSample>::value) {
+        // nobody looks at the samples: the loop in units of the step; the tube angles themselves only if they are an output
+        if (albase) sw.template run_scaled<true>();
+        else        sw.template run_scaled<false>();
+    } else {
+        sw.run();
     }
+    if (WANT_TIP && tip) finish_tip<L>(rb, c, sw, tip);
     if (albase) {
 #pragma unroll
         for (int t = 0; t < T; ++t) albase[t] = sw.al[t];
     }
+}
+
+// Two configurations with the SAME sample count solved by one thread in lock-step: two independent dependency chains
+// for the compiler to interleave, so a warp always has FP64 work ready while the other chain waits on a result.
+// Iterations in which both are hot run the two hot steps in one basic block; anything else steps them one after the
+// other.  Results are bit-identical to two solve_fast calls (same arithmetic per configuration).
+template <class L>
+CTR_HD void solve_fast_pair(const KRobot& rb, const Ctl<L>& c0, const Ctl<L>& c1, double* tip0, double* tip1)
+{
+    constexpr int T = L::T;
+    FastSweep<L, true, NoSample> A(rb, c0, NoSample{}), B(rb, c1, NoSample{});
+    const int n = c0.n;                                    // == c1.n
+    double dlA[T], dlB[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { dlA[t] = 0.0; dlB[t] = 0.0; }
+    if (n == 1) {
+        A.template step<true, true, false>(0, dlA, 0.0, 0.0);
+        B.template step<true, true, false>(0, dlB, 0.0, 0.0);
+    } else {
+        A.template step<true, false, false>(n - 1, dlA, 0.0, 0.0);
+        B.template step<true, false, false>(n - 1, dlB, 0.0, 0.0);
+#pragma unroll 1
+        for (int k = n - 2; k >= 1; --k) {
+            double sxyA, mA, sxyB, mB;
+            const int tA = A.classify(dlA, sxyA, mA);
+            const int tB = B.classify(dlB, sxyB, mB);
+            if ((tA | tB) == 0) {
+                A.template step<false, false, true, true>(k, dlA, sxyA, mA);
+                B.template step<false, false, true, true>(k, dlB, sxyB, mB);
+            } else {
+                A.step_tier(tA, k, dlA, sxyA, mA);
+                B.step_tier(tB, k, dlB, sxyB, mB);
+            }
+        }
+        {
+            double s_, m_;
+            A.classify(dlA, s_, m_); B.classify(dlB, s_, m_);       // dl only; unused by the tail
+        }
+        A.template step<false, true, false>(0, dlA, 0.0, 0.0);
+        B.template step<false, true, false>(0, dlB, 0.0, 0.0);
+    }
+    finish_tip<L>(rb, c0, A, tip0);
+    finish_tip<L>(rb, c1, B, tip1);
 }
 
 

@@ -68,9 +68,18 @@ __device__ __forceinline__ void store_tf_gather(const FkArgs& a, int64_t cfg, co
 }
 
 template <class L>
-__device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg)
+__device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg, int maxs)
 {
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    // frame 0 and radius 0 of an invalid configuration are NaN (its n_out is 0; the rest of its row is left alone)
+    if (a.backbone) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            if (a.soa) a.backbone[(int64_t)j * a.B + cfg] = qnan;
+            else       a.backbone[cfg * (int64_t)maxs * 12 + j] = qnan;
+        }
+    }
+    if (a.radius) a.radius[a.soa ? cfg : cfg * (int64_t)maxs] = qnan;
     if (a.tip) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) a.tip[cfg * 12 + j] = qnan;
@@ -110,7 +119,7 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
     load_jv<L>(a.jv, cfg, q);
     Ctl<L> c;
     setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-    if (c.status) { write_invalid<L>(a, cfg); return; }
+    if (c.status) { write_invalid<L>(a, cfg, rb.maxs); return; }
 
     double tip[12];
     double alb[L::T];
@@ -185,7 +194,7 @@ fk_tip_gather_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ 
         Ctl<L> c;
         setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
         if (c.status) {
-            write_invalid<L>(a, cfg);                  // a.tip is null here: sample count, step, status only
+            write_invalid<L>(a, cfg, rb.maxs);                  // a.tip is null here: sample count, step, status only
         } else {
             solve_fast<L, true>(rb, c, tip, nullptr, NoSample{});
             if (a.n_out) a.n_out[cfg] = c.nframes;
@@ -250,7 +259,7 @@ fk_backbone_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Fk
     load_jv<L>(a.jv, cfg, q);
     Ctl<L> c;
     setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-    if (c.status) { write_invalid<L>(a, cfg); return; }
+    if (c.status) { write_invalid<L>(a, cfg, rb.maxs); return; }
 
     ParkSample park;
     if (a.soa) { park.base = a.backbone + cfg; park.kstride = 12 * a.B; park.cstride = a.B; }
@@ -352,7 +361,7 @@ struct FrameStoreAos {       // one configuration's frames back to back: 3 full-
 
 // LAYOUT: 0 = SoA [MaxS][12][B], 1 = AoS [B][MaxS][12] with a 32-byte aligned buffer, 2 = AoS, 16-byte aligned
 template <class L, int LAYOUT>
-__global__ void __launch_bounds__(kBlock, tip_blocks_per_sm(L::T, L::S))
+__global__ void __launch_bounds__(kBlock, backbone_blocks_per_sm(L::T, L::S))
 fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -362,12 +371,12 @@ fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_cons
     load_jv<L>(a.jv, cfg, q);
     Ctl<L> c;
     setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-    if (c.status) { write_invalid<L>(a, cfg); return; }
+    if (c.status) { write_invalid<L>(a, cfg, rb.maxs); return; }
 
     QT T;
     {
         FastSweep<L, true, NoSample> s1(rb, c, NoSample{});
-        s1.run();
+        s1.template run_scaled<true>();      // the tube angles are an output (alpha_base)
         T.w = s1.Qw; T.x = s1.Qx; T.y = s1.Qy; T.z = s1.Qz; T.px = s1.Px; T.py = s1.Py; T.pz = s1.Pz;
         if (a.alpha_base) {
 #pragma unroll

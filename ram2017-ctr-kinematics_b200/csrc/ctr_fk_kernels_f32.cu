@@ -16,7 +16,7 @@ fk_tip_f32_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkA
     load_jv<L>(a.jv, cfg, q);
     Ctl<L> c;
     setup_control<L>(rb, q, a.mode, a.step, a.nsamples, c);
-    if (c.status) { write_invalid<L>(a, cfg); return; }
+    if (c.status) { write_invalid<L>(a, cfg, rb.maxs); return; }
     double tip[12];
     solve_f32<L>(rb, c, tip);
     if (a.tip) store_tf(a.tip + cfg * 12, tip);
@@ -45,8 +45,8 @@ fk_tip_f32x2_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ F
         c1 = c0;
     }
     const bool ok0 = (c0.status == 0), ok1 = has1 && (c1.status == 0);
-    if (!ok0) write_invalid<L>(a, cfg0);
-    if (has1 && !ok1) write_invalid<L>(a, cfg1);
+    if (!ok0) write_invalid<L>(a, cfg0, rb.maxs);
+    if (has1 && !ok1) write_invalid<L>(a, cfg1, rb.maxs);
     if (!ok0 && !ok1) return;
     // an invalid or absent configuration runs as a copy of its partner and is not stored
     double tip0[12], tip1[12];

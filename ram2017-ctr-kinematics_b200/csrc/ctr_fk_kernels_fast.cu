@@ -1,5 +1,6 @@
-// ctr_fk_kernels_fast.cu — instantiates the solver kernels with FAST arithmetic (series SE(3) step, quaternion accumulation, custom sin/cos)
-// for all 14 section layouts.
+// ctr_fk_kernels_fast.cu — the tip kernel with FAST arithmetic (series SE(3) step, quaternion accumulation, custom
+// sin/cos) for all 14 section layouts.  The gather and backbone kernels are instantiated in their own translation units
+// (ctr_fk_kernels_gather.cu, ctr_fk_kernels_backbone.cu) so that the three compile in parallel.
 #include "ctr_fk_kernels.cuh"
 #include "ctr_fk_internal.h"
 
@@ -18,49 +19,6 @@ cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& args, cudaS
     }
     switch (key) {
 #define X(S, A, Bq, C) CTRK_LAUNCH_CASE(fk_tip_kernel, true, S, A, Bq, C)
-        CTRK_FOR_EACH_LAYOUT_K(X)
-#undef X
-        default: return cudaErrorInvalidValue;
-    }
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tip_gather(int key, const KRobot& rb, const FkArgs& args, cudaStream_t st)
-{
-    if (args.B <= 0) return cudaSuccess;
-    FkArgs a = args;
-    unsigned grid = grid_for(a.B);
-    if (a.order) {
-        a.windows = (int)((a.B + kBinWindow - 1) / kBinWindow);
-        grid = (unsigned)a.windows * (kBinWindow / kBlock);
-    }
-    switch (key) {
-#define X(S, A, Bq, C) \
-    case S * 1000 + A * 100 + Bq * 10 + C: \
-        fk_tip_gather_kernel<Lay<S, A, Bq, C>><<<grid, kBlock, 0, st>>>(rb, a); \
-        break;
-        CTRK_FOR_EACH_LAYOUT_K(X)
-#undef X
-        default: return cudaErrorInvalidValue;
-    }
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st)
-{
-    if (a.B <= 0) return cudaSuccess;
-    const unsigned grid = grid_for(a.B);
-    // one kernel for every layout: two sweeps per thread, frames emitted as the second sweep passes
-    const int layout = a.soa ? 0 : ((reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0 ? 1 : 2);
-    switch (key) {
-#define X(S, A, Bq, C) \
-    case S * 1000 + A * 100 + Bq * 10 + C: \
-        if (layout == 0)      fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 0><<<grid, kBlock, 0, st>>>(rb, a); \
-        else if (layout == 1) fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 1><<<grid, kBlock, 0, st>>>(rb, a); \
-        else                  fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 2><<<grid, kBlock, 0, st>>>(rb, a); \
-        break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X
         default: return cudaErrorInvalidValue;

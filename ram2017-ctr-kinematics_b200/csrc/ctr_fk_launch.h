@@ -86,8 +86,12 @@ constexpr int kBlock = 128;     // threads per CTA for every solver kernel
 // kernel's rate does not depend on the warp count between 8 and 16 warps/SM (it is bound by the FP64 pipe, not by
 // latency: tools/tune_tip.cu, 1M configurations, N=256: 3 tubes 2.008 / 1.998 ms at 12 / 16 warps; 4 tubes 2.388 /
 // 2.494; 5 tubes 2.794 / 2.912; 6 tubes 3.289 / 3.463; 3 tubes in 3 sections 2.074 / 2.089 with an 8-byte spill at 128 registers), so
-// those layouts get up to 168 registers and 3 CTAs.
-constexpr int tip_blocks_per_sm(int ntubes, int nsections) { return (ntubes >= 4 || nsections >= 3) ? 3 : 4; }
+// those layouts get up to 168 registers and 3 CTAs.  Round 2 (loop in units of the step, two iterations per trip, tools/tune_tip.cu):
+// 3 tubes 1.846 / 1.858 ms at 12 / 16 warps, 3 tubes in 3 sections 1.964 / 1.957, 4 tubes 2.341 / 2.340, 5 tubes 2.664 / 2.767 / 2.718
+// at 8 / 12 / 16 warps: three-tube layouts go to 3 CTAs as well, 5 and 6 tubes to 2 CTAs (up to 255 registers).
+constexpr int tip_blocks_per_sm(int ntubes, int nsections) { return ntubes >= 5 ? 2 : ((ntubes >= 3 || nsections >= 3) ? 3 : 4); }
+// the backbone kernel keeps 12 warps/SM on the large layouts: its stores want more warps in flight than the tip sweep
+constexpr int backbone_blocks_per_sm(int ntubes, int nsections) { return (ntubes >= 4 || nsections >= 3) ? 3 : 4; }
 constexpr int kBinWindow = 4096;        // step-mode binning sorts windows of this many consecutive configurations
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)

@@ -19,9 +19,10 @@ FLAG_GATHER_MULTICAST = 0x200
 FLAG_GATHER_ROWWISE = 0x400
 FLAG_HOST_STAGED = 0x800
 FLAG_RK4 = 0x1000
+FLAG_F32 = 0x2000
 HOST_WRITE_COMBINED = 1
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
-E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM = -1, -2, -3, -4, -5
+E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM, E_RANGE = -1, -2, -3, -4, -5, -6
 STATUS_OK, STATUS_PHI_RANGE = 0, 1
 SCALE_NONE, SCALE_GAMMA, SCALE_PROPORTIONAL = 0, 1, 2
 SHOOT_OK, SHOOT_PHI_RANGE, SHOOT_SINGULAR, SHOOT_MAX_ITER, SHOOT_STALLED = 0, 1, 2, 3, 4
@@ -250,7 +251,7 @@ class Engine:
         rc = load().ctr_fk_single(self.handle, _ptr(jv), mode, step, nsamples, flags, _ptr(tip),
                                   _ptr(backbone), _ptr(radius), _ptr(n_out), _ptr(step_out),
                                   _ptr(alpha_base))
-        if rc not in (0, STATUS_PHI_RANGE):
+        if rc not in (0, E_RANGE):
             _check(rc)
         return rc
 

@@ -110,7 +110,7 @@ Transform Robot::solve_single(const double* jv, int mode, double step, std::size
     double h = 0.0;
     int rc = ctr_fk_single(engine_, jv, mode, step, (int32_t)ns, 0u, tip.m, frames_.data(), radius_.data(), &n, &h,
                            alpha_base_.data());
-    if (rc < 0 || rc > CTR_FK_STATUS_PHI_RANGE) std::cerr << "ERROR: calcKinematic: " << ctr_fk_last_error() << std::endl;
+    if (rc != 0 && rc != CTR_FK_E_RANGE) std::cerr << "ERROR: calcKinematic: " << ctr_fk_last_error() << std::endl;
     nsamples_ = (std::size_t)(n > 0 ? n : 0);
     last_jv_.assign(jv, jv + getNJointValues());
     if (stepReturn) *stepReturn = h;
@@ -203,6 +203,90 @@ void Robot::getRandomJointValues(CT_RNG& rng, CT_RND& rnd, VectorJ& jv) const
         for (int k = 0; k < desc_.sec[s].ntube; ++k) jv[2 + s + t0 + k] = c * rnd(rng);
         t0 += (std::size_t)desc_.sec[s].ntube;
     }
+}
+
+void Robot::getRandomJointValues(CT_RNG& rng, CT_RND& rnd, VectorJ& jv, const TransRotScale& ts) const
+{
+    if (!engine_) { fool(__func__); return; }
+    jv.assign(getNJointValues(), 0.0);
+    const double c = std::nextafter(2.0 * M_PI, 0.0);
+    jv[0] = c * rnd(rng);
+    std::size_t t0 = 0;
+    for (int s = 0; s < desc_.nsections; ++s) {                         // section_i.h:341-346
+        jv[1 + s + t0] = desc_.sec[s].length * ts.scaleTrans(rnd(rng));
+        for (int k = 0; k < desc_.sec[s].ntube; ++k) jv[2 + s + t0 + k] = c * rnd(rng);
+        t0 += (std::size_t)desc_.sec[s].ntube;
+    }
+}
+
+bool ProportionalScale::initialize(const Robot& robot)
+{
+    if (!robot.init()) return false;
+    lengths_.clear();
+    total_ = 0.0;
+    for (std::size_t s = 0; s < robot.getNSections(); ++s) {
+        ctr_section_desc sd;
+        if (!robot.getSection((unsigned)s, &sd)) return false;
+        lengths_.push_back(sd.length);
+        total_ += sd.length;
+    }
+    section_ = 0;
+    room_ = total_;
+    redraw((double)std::rand() / (double)RAND_MAX);
+    return true;
+}
+
+bool Robot::setMaxSample(std::size_t maxSample)
+{
+    if (maxSample == 0 || !engine_) return false;
+    if ((std::size_t)desc_.max_samples == maxSample) return true;
+    ctr_robot_desc nd = desc_;
+    nd.max_samples = (int32_t)maxSample;
+    ctr_fk_handle ne = nullptr;
+    if (ctr_fk_create(&nd, device_, &ne) != 0) return false;           // the old robot stays usable, like a failed malloc
+    ctr_fk_destroy(engine_);
+    engine_ = ne;
+    desc_ = nd;
+    nsamples_ = 0;
+    frames_.assign(maxSample * 12, 0.0);
+    radius_.assign(maxSample, 0.0);
+    return true;
+}
+
+int RobotF::solve(const float* jv, std::int64_t B, int mode, double step, std::size_t ns, float* tip, std::int32_t* nOut,
+                  double* stepOut)
+{
+    if (!r_.init()) { fool(__func__); return CTR_FK_E_NULL; }
+    const std::size_t nj = r_.getNJointValues();
+    std::vector<double> q((std::size_t)B * nj), t((std::size_t)B * 12), h((std::size_t)B);
+    for (std::size_t i = 0; i < q.size(); ++i) q[i] = (double)jv[i];
+    int rc = ctr_fk_batch_host(r_.handle(), q.data(), B, mode, step, (int32_t)ns, CTR_FK_FLAG_F32, t.data(), nOut, h.data(), nullptr);
+    if (rc) { std::cerr << "ERROR: calcKinematic: " << ctr_fk_last_error() << std::endl; return rc; }
+    for (std::size_t i = 0; i < t.size(); ++i) tip[i] = (float)t[i];
+    if (stepOut && B > 0) *stepOut = h[0];
+    return 0;
+}
+TransformF RobotF::calcKinematic(const VectorJF& jv, const float& step, float& stepReturn)
+{
+    TransformF t; for (int i = 0; i < 12; ++i) t.m[i] = (i % 4 == 0 && i < 9) ? 1.f : 0.f;
+    if (jv.size() < getNJointValues()) { std::cerr << "ERROR: calcKinematic: joint vector too short" << std::endl; return t; }
+    std::int32_t n = 0; double h = 0.0;
+    if (solve(jv.data(), 1, CTR_FK_MODE_STEP, (double)step, 0, t.m, &n, &h) == 0) { nsamples_ = (std::size_t)(n > 0 ? n : 0); stepReturn = (float)h; }
+    return t;
+}
+TransformF RobotF::calcKinematic(const VectorJF& jv, const float& step) { float r; return calcKinematic(jv, step, r); }
+TransformF RobotF::calcKinematic(const VectorJF& jv, const std::size_t& ns, float& stepReturn)
+{
+    TransformF t; for (int i = 0; i < 12; ++i) t.m[i] = (i % 4 == 0 && i < 9) ? 1.f : 0.f;
+    if (jv.size() < getNJointValues()) { std::cerr << "ERROR: calcKinematic: joint vector too short" << std::endl; return t; }
+    std::int32_t n = 0; double h = 0.0;
+    if (solve(jv.data(), 1, CTR_FK_MODE_NSAMPLE, 0.0, ns, t.m, &n, &h) == 0) { nsamples_ = (std::size_t)(n > 0 ? n : 0); stepReturn = (float)h; }
+    return t;
+}
+TransformF RobotF::calcKinematic(const VectorJF& jv, const std::size_t& ns) { float r; return calcKinematic(jv, ns, r); }
+int RobotF::calcKinematicBatch(const float* jv, std::int64_t B, const std::size_t& ns, float* tip, std::int32_t* nOut)
+{
+    return solve(jv, B, CTR_FK_MODE_NSAMPLE, 0.0, ns, tip, nOut, nullptr);
 }
 
 void Robot::calcJacobian(const VectorJ& jv, const std::size_t& ns, const double& fdTrans, const double& fdRot, MatJacobian& J)

@@ -56,6 +56,11 @@ void run(const KRobot& rb, const double* jv, int64_t B, int mode, double step, i
         if (fast == 2) {       // FP32 variant (no alpha_base / samples)
             solve_f32<L>(rb, c, t);
             for (int q = 0; q < L::T; ++q) ab[q] = 0.0;
+        } else if (fast == 4) {   // nobody looks at the samples: the loop in units of the step (FastSweep::run_scaled<true>)
+            solve_fast<L, true>(rb, c, t, ab, NoSample{});
+        } else if (fast == 5) {   // ... without the tube angles as an output (run_scaled<false>)
+            solve_fast<L, true>(rb, c, t, nullptr, NoSample{});
+            for (int q = 0; q < L::T; ++q) ab[q] = 0.0;
         } else if (fast) solve_fast<L, true>(rb, c, t, ab, park);
         else             solve_strict<L, true>(rb, c, t, ab, park);
         if (tip) std::memcpy(tip + 12 * i, t, sizeof t);
@@ -240,5 +245,11 @@ extern "C" void hostsim_tier_counters(long long* out3, int reset)
 {
     out3[0] = g_iter_total; out3[1] = g_iter_cold; out3[2] = g_iter_cold_delta;
     if (reset) g_iter_total = g_iter_cold = g_iter_cold_delta = 0;
+}
+// iterations of run_scaled's loop, and how many of them hot
+extern "C" void hostsim_block_counters(long long* out2, int reset)
+{
+    out2[0] = g_iter_block; out2[1] = g_iter_blockhot;
+    if (reset) g_iter_block = g_iter_blockhot = 0;
 }
 #endif

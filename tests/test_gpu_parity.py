@@ -294,6 +294,9 @@ def test_host_pointer_batch_and_single(ctrfk, oracle, robots, engines):
         assert np.array_equal(rd[: r["n"]], r["radius"])
         assert np.abs(ab - r["alpha_base"]).max() < 1e-9
         assert np.array_equal(t1, bb[r["n"] - 1])
+    qbad = jv[0].copy(); qbad[1] = -0.5                      # Phi out of range: a code of its own, NaN outputs
+    t1 = np.zeros(12)
+    assert eng.single(qbad, 1, nsamples=64, tip=t1) == ctrfk.E_RANGE and np.isnan(t1).all()
 
 
 @pytest.mark.parametrize("name", ["ctr_sec2_tub3.xml", "ctr_sec3_tub3.xml"])      # even and odd joint counts

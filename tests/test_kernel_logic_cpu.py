@@ -29,6 +29,44 @@ def test_solvers_match_oracle(ctrfk, oracle, hostsim, robots, name, fast):
         assert np.abs(o["alpha_base"] - s["alpha_base"]).max() < 1e-10
 
 
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+@pytest.mark.parametrize("fast", [4, 5], ids=["with_base_angles", "tip_only"])
+def test_scaled_loop_matches_oracle(ctrfk, oracle, hostsim, robots, name, fast):
+    """FastSweep::run_scaled — the loop the tip, gather, Jacobian (tip forms) and stability kernels run when nobody
+    looks at the samples: state in units of the step, tube angles not accumulated in the tip-only form.  Same gate as
+    the FAST solver; sample counts and steps exact; base angles (fast = 4) as before.  Coarse sampling mixes hot and
+    generic iterations (conversions in both directions), N = 7 and N = 1 take run() itself."""
+    d = robots[name]
+    jv = np.vstack([ctrfk.sample_joints_host(d, util.SEEDS[name], 0, 3000), util.edge_joint_sets(d)])
+    for mode, kw in ((ctrfk.MODE_NSAMPLE, dict(nsamples=256)), (ctrfk.MODE_STEP, dict(step=d.max_length / 256.0)),
+                     (ctrfk.MODE_NSAMPLE, dict(nsamples=1)), (ctrfk.MODE_NSAMPLE, dict(nsamples=7)),
+                     (ctrfk.MODE_NSAMPLE, dict(nsamples=24)), (ctrfk.MODE_NSAMPLE, dict(nsamples=64)),
+                     (ctrfk.MODE_STEP, dict(step=0.01)), (ctrfk.MODE_STEP, dict(step=2e-5))):
+        o = oracle.fk_batch(d, jv, mode, **kw)
+        s = util.hostsim_fk(hostsim, d, jv, mode, fast=fast, **kw)
+        assert np.array_equal(o["n"], s["n"]) and np.array_equal(o["step"], s["step"])
+        dp, ang = util.pose_errors(o["tip"], s["tip"])
+        assert dp.max() < 2e-10 and ang.max() < 1e-11, (mode, kw, dp.max(), ang.max())
+        if fast == 4:
+            assert np.abs(o["alpha_base"] - s["alpha_base"]).max() < 1e-10
+        # ... and against the loop it replaces: the same arithmetic up to the placement of the factor h
+        r = util.hostsim_fk(hostsim, d, jv, mode, fast=1, **kw)
+        dp, ang = util.pose_errors(r["tip"], s["tip"])
+        assert dp.max() < 1e-12 and ang.max() < 1e-12, (mode, kw, dp.max(), ang.max())
+
+
+def test_scaled_loop_pose_does_not_depend_on_the_base_angle_output(ctrfk, hostsim, robots):
+    """Both forms of run_scaled (tube angles accumulated or not) give the same bits: generic iterations take their
+    angles modulo 2 pi from the carried sin/cos in both — so ctr_fk_batch (which can return alpha_base) and the
+    zero-copy host call (which cannot) agree bit for bit, coarse sampling included."""
+    d = robots["ctr_sec3_tub5.xml"]
+    jv = ctrfk.sample_joints_host(d, 5, 0, 4000)
+    for n in (24, 48, 128, 256):
+        a = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=n, fast=4)
+        b = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=n, fast=5)
+        assert np.array_equal(a["tip"], b["tip"])
+
+
 def test_coarse_steps_take_the_closed_form_branch(ctrfk, oracle, hostsim, robots):
     """h|u| > 0.5 rad per step: FAST leaves the series for the closed form."""
     d = robots["ctr_sec2_tub3.xml"]

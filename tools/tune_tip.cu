@@ -29,6 +29,31 @@ tip_variant(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
     store_tf(a.tip + i * 12, tip);
 }
 
+// two configurations per thread (solve_fast_pair): thread i solves i and i + half
+template <class L, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+tip_pair_variant(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
+{
+    const int64_t half = (a.B + 1) / 2;
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= half) return;
+    const int64_t j = (i + half < a.B) ? i + half : i;
+    double q0[L::NJ], q1[L::NJ];
+    load_jv<L>(a.jv, i, q0);
+    load_jv<L>(a.jv, j, q1);
+    Ctl<L> c0, c1;
+    setup_control<L>(rb, q0, a.mode, a.step, a.nsamples, c0);
+    setup_control<L>(rb, q1, a.mode, a.step, a.nsamples, c1);
+    if (c0.status || c1.status || c0.n != c1.n) return;
+    double t0[12], t1[12];
+    solve_fast_pair<L>(rb, c0, c1, t0, t1);
+    store_tf(a.tip + i * 12, t0);
+    store_tf(a.tip + j * 12, t1);
+}
+
+template <class L, int BLOCK, int MINB>
+void run_pair(const KRobot& rb, FkArgs a, const char* tag);
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
 template <class L, int BLOCK, int MINB>
@@ -53,6 +78,31 @@ void run(const KRobot& rb, FkArgs a, const char* tag)
         if (ms < best) best = ms;
     }
     printf("%-10s block %3d minb %2d regs %3d local %4zu occ %2d blocks (%2d warps/SM)  %.3f ms  %.3e cfg/s\n", tag, BLOCK, MINB,
+           fa.numRegs, fa.localSizeBytes, occ, occ * BLOCK / 32, best, a.B / (best * 1e-3));
+}
+
+template <class L, int BLOCK, int MINB>
+void run_pair(const KRobot& rb, FkArgs a, const char* tag)
+{
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, tip_pair_variant<L, BLOCK, MINB>));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tip_pair_variant<L, BLOCK, MINB>, BLOCK, 0));
+    const unsigned grid = (unsigned)(((a.B + 1) / 2 + BLOCK - 1) / BLOCK);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) tip_pair_variant<L, BLOCK, MINB><<<grid, BLOCK>>>(rb, a);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CK(cudaEventRecord(e0));
+        tip_pair_variant<L, BLOCK, MINB><<<grid, BLOCK>>>(rb, a);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    printf("%-10s PAIR block %3d minb %2d regs %3d local %4zu occ %2d blocks (%2d warps/SM)  %.3f ms  %.3e cfg/s\n", tag, BLOCK, MINB,
            fa.numRegs, fa.localSizeBytes, occ, occ * BLOCK / 32, best, a.B / (best * 1e-3));
 }
 
@@ -95,6 +145,9 @@ int main(int argc, char** argv)
 #define TUNE_TAG "cur"
 #endif
     if (which == 0) { run<Lay<2, 2, 1, 0>, 128, 3>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 128, 4>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 128, 5>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 64, 8>(rb, a, TUNE_TAG); run<Lay<2, 2, 1, 0>, 64, 10>(rb, a, TUNE_TAG); }
+    if (which == 0) { run_pair<Lay<2, 2, 1, 0>, 128, 2>(rb, a, TUNE_TAG); run_pair<Lay<2, 2, 1, 0>, 64, 4>(rb, a, TUNE_TAG); run_pair<Lay<2, 2, 1, 0>, 64, 5>(rb, a, TUNE_TAG); run_pair<Lay<2, 2, 1, 0>, 64, 6>(rb, a, TUNE_TAG); run_pair<Lay<2, 2, 1, 0>, 32, 8>(rb, a, TUNE_TAG); }
+    if (which == 1) { run_pair<Lay<3, 1, 1, 1>, 128, 2>(rb, a, TUNE_TAG); run_pair<Lay<3, 1, 1, 1>, 64, 5>(rb, a, TUNE_TAG); }
+    if (which == 2) { run_pair<Lay<3, 2, 2, 1>, 128, 2>(rb, a, TUNE_TAG); run_pair<Lay<3, 2, 2, 1>, 64, 4>(rb, a, TUNE_TAG); }
     if (which == 1) { run<Lay<3, 1, 1, 1>, 128, 3>(rb, a, TUNE_TAG); run<Lay<3, 1, 1, 1>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 1, 1, 1>, 128, 5>(rb, a, TUNE_TAG); }
     if (which == 3) { run<Lay<3, 2, 1, 1>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 2, 1, 1>, 128, 3>(rb, a, TUNE_TAG); }
     if (which == 4) { run<Lay<3, 2, 2, 2>, 128, 4>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 2>, 128, 3>(rb, a, TUNE_TAG); run<Lay<3, 2, 2, 2>, 128, 2>(rb, a, TUNE_TAG); }
