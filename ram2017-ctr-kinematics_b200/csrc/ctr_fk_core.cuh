@@ -963,6 +963,10 @@ struct FastSweep {
     // of the loop control disappear (tools/tune_tip.cu: 1.89 -> 1.85 ms per 1M on the 3-tube robot, 2.86 -> 2.72 on
     // the 5-tube one)
     static constexpr int kScaledUnroll = CTRK_SCALED_UNROLL;
+#ifndef CTRK_EMIT_UNROLL
+#define CTRK_EMIT_UNROLL 1
+#endif
+    static constexpr int kEmitUnroll = CTRK_EMIT_UNROLL;
 
     // one hot iteration; dl[t] = w_t - w_0, (sxy, m) = |psi_xy|^2, |psi|^2 of the pending sample (pux, puy, puz = psi)
     template <bool KEEP_AL>
@@ -1169,7 +1173,7 @@ struct FastSweep {
             step<true, true, false>(0, dl, 0.0, 0.0);
         } else {
             step<true, false, false>(n - 1, dl, 0.0, 0.0);
-#pragma unroll 1
+#pragma unroll kEmitUnroll
             for (int k = n - 2; k >= 1; --k) {
                 int dmax = 0, amax = 0;
                 const double z0 = uzs[0];
