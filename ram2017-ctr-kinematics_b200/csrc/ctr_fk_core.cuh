@@ -963,10 +963,13 @@ struct FastSweep {
     // of the loop control disappear (tools/tune_tip.cu: 1.89 -> 1.85 ms per 1M on the 3-tube robot, 2.86 -> 2.72 on
     // the 5-tube one)
     static constexpr int kScaledUnroll = CTRK_SCALED_UNROLL;
-#ifndef CTRK_EMIT_UNROLL
-#define CTRK_EMIT_UNROLL 1
-#endif
+    // run_emit: two iterations per trip where the kernel has the registers for it (layouts that run at 2 CTAs per SM,
+    // backbone_blocks_per_sm): 6.46 -> 6.38 ms per 1M x 256 frames; at 168 registers it is slower (7.39 against 6.95)
+#ifdef CTRK_EMIT_UNROLL
     static constexpr int kEmitUnroll = CTRK_EMIT_UNROLL;
+#else
+    static constexpr int kEmitUnroll = (T >= 4 || S >= 3) ? 2 : 1;
+#endif
 
     // one hot iteration; dl[t] = w_t - w_0, (sxy, m) = |psi_xy|^2, |psi|^2 of the pending sample (pux, puy, puz = psi)
     template <bool KEEP_AL>

@@ -1,5 +1,5 @@
-// ctr_fk_kernels_backbone.cu — the two-sweep backbone kernel (FAST arithmetic; SoA, 32-byte and 16-byte aligned AoS
-// forms) for all 14 section layouts.
+// ctr_fk_kernels_backbone.cu — the two-sweep backbone kernel, AoS output ([B][MaxS][12]; 32-byte and 16-byte aligned
+// forms), all 14 section layouts.  The SoA form is instantiated in ctr_fk_kernels_backbone_soa.cu.
 #include "ctr_fk_kernels.cuh"
 #include "ctr_fk_internal.h"
 
@@ -12,12 +12,12 @@ cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cud
     if (a.B <= 0) return cudaSuccess;
     const unsigned grid = grid_for(a.B);
     // one kernel for every layout: two sweeps per thread, frames emitted as the second sweep passes
-    const int layout = a.soa ? 0 : ((reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0 ? 1 : 2);
+    if (a.soa) return launch_backbone_fast_soa(key, rb, a, st);      // ctr_fk_kernels_backbone_soa.cu
+    const int layout = (reinterpret_cast<uintptr_t>(a.backbone) & 31) == 0 ? 1 : 2;
     switch (key) {
 #define X(S, A, Bq, C) \
     case S * 1000 + A * 100 + Bq * 10 + C: \
-        if (layout == 0)      fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 0><<<grid, kBlock, 0, st>>>(rb, a); \
-        else if (layout == 1) fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 1><<<grid, kBlock, 0, st>>>(rb, a); \
+        if (layout == 1) fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 1><<<grid, kBlock, 0, st>>>(rb, a); \
         else                  fk_backbone_twosweep_kernel<Lay<S, A, Bq, C>, 2><<<grid, kBlock, 0, st>>>(rb, a); \
         break;
         CTRK_FOR_EACH_LAYOUT_K(X)

@@ -30,7 +30,9 @@ fk_jacobian_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ Ja
                        a.n_out ? a.n_out + cfg : nullptr, a.given != 0);
 }
 
-template <bool FAST>
+// WITH_SAMPLE picks the instantiation family: the iSample forms (two Jacobians, sample product next to the tip product)
+// and the tip-only forms are compiled in separate translation units (each takes minutes for 14 layouts)
+template <bool FAST, bool WITH_SAMPLE>
 cudaError_t launch_jacobian_t(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st)
 {
     if (a.B <= 0) return cudaSuccess;
@@ -38,8 +40,7 @@ cudaError_t launch_jacobian_t(int key, const KRobot& rb, const JacArgs& a, cudaS
     switch (key) {
 #define X(S, A, Bq, C) \
     case S * 1000 + A * 100 + Bq * 10 + C: \
-        if (a.i_sample >= 0) fk_jacobian_kernel<Lay<S, A, Bq, C>, true, FAST><<<grid, kBlock, 0, st>>>(rb, a); \
-        else                 fk_jacobian_kernel<Lay<S, A, Bq, C>, false, FAST><<<grid, kBlock, 0, st>>>(rb, a); \
+        fk_jacobian_kernel<Lay<S, A, Bq, C>, WITH_SAMPLE, FAST><<<grid, kBlock, 0, st>>>(rb, a); \
         break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X

@@ -35,7 +35,7 @@ cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, c
 }
 
 // CTR_FK_FLAG_STRICT forms of the Jacobian and stability calls: every solve inside them is the STRICT solver
-cudaError_t launch_jacobian_strict(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st) { return launch_jacobian_t<false>(key, rb, a, st); }
+cudaError_t launch_jacobian_strict(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st) { return a.i_sample >= 0 ? launch_jacobian_t<false, true>(key, rb, a, st) : launch_jacobian_t<false, false>(key, rb, a, st); }
 cudaError_t launch_stability_strict(int key, const KRobot& rb, const StabArgs& a, int sm_count, cudaStream_t st)
 {
     return launch_stability_t<false>(key, rb, a, sm_count, st);

@@ -90,8 +90,14 @@ constexpr int kBlock = 128;     // threads per CTA for every solver kernel
 // 3 tubes 1.846 / 1.858 ms at 12 / 16 warps, 3 tubes in 3 sections 1.964 / 1.957, 4 tubes 2.341 / 2.340, 5 tubes 2.664 / 2.767 / 2.718
 // at 8 / 12 / 16 warps: three-tube layouts go to 3 CTAs as well, 5 and 6 tubes to 2 CTAs (up to 255 registers).
 constexpr int tip_blocks_per_sm(int ntubes, int nsections) { return ntubes >= 5 ? 2 : ((ntubes >= 3 || nsections >= 3) ? 3 : 4); }
-// the backbone kernel keeps 12 warps/SM on the large layouts: its stores want more warps in flight than the tip sweep
-constexpr int backbone_blocks_per_sm(int ntubes, int nsections) { return (ntubes >= 4 || nsections >= 3) ? 3 : 4; }
+#ifdef CTRK_BB_MINB      /* tools/tune_bb.cu only */
+constexpr int backbone_blocks_per_sm(int, int) { return CTRK_BB_MINB; }
+#else
+// round 2 (tools/tune_bb.cu, ctr_sec3_tub4, 1M x 256 frames): 7.49 / 6.95 / 6.46 ms at 4 / 3 / 2 CTAs per SM (128 / 168 / 224
+// registers) and 6.38 ms with two iterations per trip at 2 CTAs: the emitter's 12-double frame, the walked product and
+// the sweep state want ~220 registers; with them the constant loads and register copies of the 168-register build go
+constexpr int backbone_blocks_per_sm(int ntubes, int nsections) { return (ntubes >= 4 || nsections >= 3) ? 2 : 3; }
+#endif
 constexpr int kBinWindow = 4096;        // step-mode binning sorts windows of this many consecutive configurations
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
@@ -101,6 +107,7 @@ cudaError_t launch_tip_strict(int key, const KRobot& rb, const FkArgs& a, cudaSt
 cudaError_t launch_tip_f32(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 // backbone solvers (two passes inside one kernel; the output buffer doubles as scratch)
 cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+cudaError_t launch_backbone_fast_soa(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 // finite-difference Jacobian (fast arithmetic)
 cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);
