@@ -74,7 +74,8 @@ def parse():
     ap.add_argument("--config-steps", type=int, default=6, help="timed steps of every `configs` entry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer end-to-end leg (very large batches)")
-    ap.add_argument("--e2e-staged", action="store_true", help="e2e through the chunked copy pipeline (CTR_FK_FLAG_HOST_STAGED) instead of zero-copy")
+    ap.add_argument("--e2e-staged", action="store_true", help="e2e through the chunked copy pipeline (the default form; kept for old command lines)")
+    ap.add_argument("--e2e-zerocopy", action="store_true", help="e2e through the zero-copy form (CTR_FK_FLAG_HOST_ZEROCOPY): one kernel reads and writes page-locked host memory")
     ap.add_argument("--e2e-wc", action="store_true", help="e2e: joint vectors in write-combined host memory")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the CPUs local to its GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="configurations of the CPU baseline sample (0 = auto)")
@@ -620,7 +621,7 @@ def run_e2e(ctx, a, w, live):
     eng, desc = live["eng"], live["desc"]
     B, njv = w.batch, desc.njoints
     mode, step_len = live["mode"], live["step_len"]
-    flags = live["flags"] | (ctrfk.FLAG_HOST_STAGED if a.e2e_staged else 0)
+    flags = live["flags"] | (ctrfk.FLAG_HOST_STAGED if a.e2e_staged else 0) | (ctrfk.FLAG_HOST_ZEROCOPY if a.e2e_zerocopy else 0)
 
     # this process on the CPUs next to its GPU before any pinned page is touched (multi-socket hosts)
     bound = None
@@ -708,12 +709,12 @@ def run_e2e(ctx, a, w, live):
     torch.cuda.synchronize()
     same = bool(np.array_equal(h_tip, live["tips"][0].cpu().numpy()))
     assert np.isfinite(h_tip).all() and same, "end-to-end poses differ from the device-resident path"
-    zero_copy = not (a.e2e_staged or w.strict or (w.mode == "S" and B >= 8192))
+    zero_copy = a.e2e_zerocopy and not (a.e2e_staged or w.strict or (w.mode == "S" and B >= 8192))
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * njv * 8, "d2h_bytes_per_step": B * 12 * 8,
            "steps": e2e_steps,
            "api": "ctr_fk_batch_host (host pointers in, tip poses out; " +
                   ("zero-copy form: ONE kernel reads the joint vectors from and writes the poses to page-locked host memory over PCIe"
-                   if zero_copy else "staged form: chunked H2D/solve/D2H on 4 streams") + ")",
+                   if zero_copy else "staged form: wave-sized chunks copied in, solved and copied out on 4 streams (both copy engines and the SMs busy at once)") + ")",
            "host_buffers": "ctr_fk_host_alloc: page-locked, device-mapped, first-touched on the CPUs local to the GPU" +
                            (", joint vectors write-combined" if a.e2e_wc else ""),
            "cpu_binding": ("process bound to GPU-local CPUs %s" % bound[1]) if bound else "none needed (the GPU's local CPU list covers the process's CPUs, or is unknown)",

@@ -155,17 +155,20 @@ int ctr_fk_batch_f32(ctr_fk_handle h, const double* jv, int64_t B, int mode, dou
                      double* tip, int32_t* n_out, double* step_out, int32_t* status, void* stream);
 
 /* Batched FK with HOST pointers (pageable or pinned).  Synchronous: returns when all outputs are in
- * host memory.  Two forms, chosen per call:
- *   - zero-copy (every buffer page-locked — cudaHostAlloc / cudaHostRegister / torch pin_memory() — and
- *     16-byte aligned, FAST arithmetic): ONE kernel launch reads the joint vectors from and writes the
- *     poses to host memory directly, whole lines at a time; PCIe runs in both directions under the
- *     arithmetic for the whole batch.  CTR_FK_FLAG_HOST_STAGED (or CTRFK_HOST_ZEROCOPY=0 in the
- *     environment at ctr_fk_create) selects the other form.
- *   - staged (pageable memory, STRICT): the batch is cut into chunks that are copied in, solved and
- *     copied out on rotating streams so that PCIe transfers overlap the kernels.
+ * host memory.  Two forms:
+ *   - staged (default): the batch is cut into chunks of one wave of the solver kernel that are copied in, solved and
+ *     copied out on rotating streams, so that both copy engines and the SMs work at the same time (page-locked
+ *     buffers — cudaHostAlloc / cudaHostRegister / torch pin_memory() / ctr_fk_host_alloc — make the copies
+ *     asynchronous; pageable memory works, slower).
+ *   - zero-copy (CTR_FK_FLAG_HOST_ZEROCOPY, or CTRFK_HOST_ZEROCOPY=1 in the environment at ctr_fk_create; every
+ *     buffer page-locked and 16-byte aligned, FAST arithmetic, no step-mode binning — otherwise the call falls back
+ *     to the staged form): ONE kernel launch reads the joint vectors from and writes the poses to host memory
+ *     directly, whole lines at a time; no device staging memory.  Results are bit-identical in both forms.
+ *     CTR_FK_FLAG_HOST_STAGED overrides the environment.
  * Only tip / n_out / step_out / status are offered here (backbone output is 26 KB per configuration
  * and is meant to stay on the device; see ctr_fk_batch_host_backbone). */
-#define CTR_FK_FLAG_HOST_STAGED 0x800u
+#define CTR_FK_FLAG_HOST_STAGED   0x800u
+#define CTR_FK_FLAG_HOST_ZEROCOPY 0x4000u
 /* ctr_fk_batch_host only: the FP32 state arithmetic of ctr_fk_batch_f32 (chunked copy pipeline; doubles at the
  * interface) — what ctrb200::RobotF, the shape of the reference's CTR::Robot<float>, calls */
 #define CTR_FK_FLAG_F32         0x2000u

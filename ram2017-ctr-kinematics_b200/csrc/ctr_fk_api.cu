@@ -31,8 +31,10 @@ struct ctr_fk_engine {
     int            sm_count;
     static constexpr int kStreams = 8;      // created; ctr_fk_batch_host uses host_streams of them
     int            host_streams; // pipeline depth of the host-pointer path (4; CTRFK_HOST_STREAMS overrides, for tuning)
+    int            host_chunk_div;   // ... divided by this (1; CTRFK_HOST_CHUNK_DIV, for tuning)
     int            host_chunk_waves; // chunk size of the host-pointer path in waves of the tip kernel (1; CTRFK_HOST_CHUNK_WAVES)
-    int            host_zero_copy;   // page-locked host buffers are accessed by the kernel directly (1; CTRFK_HOST_ZEROCOPY=0 disables)
+    int            host_zero_copy;   // take the zero-copy form of ctr_fk_batch_host without being asked by CTR_FK_FLAG_HOST_ZEROCOPY
+                                     // (0; CTRFK_HOST_ZEROCOPY=1 in the environment sets it)
     cudaStream_t   streams[kStreams];
     std::mutex     host_mu;      // serialises ctr_fk_batch_host / ctr_fk_single calls on one handle
     char*          single_buf;   // device scratch of ctr_fk_single (lazily allocated)
@@ -207,8 +209,10 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
     for (int i = 0; i < ctr_fk_engine::kStreams; ++i) h->streams[i] = nullptr;
     h->host_streams = 4;
     h->host_chunk_waves = 1;
+    h->host_chunk_div = 1;
+    if (const char* ev = std::getenv("CTRFK_HOST_CHUNK_DIV")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) h->host_chunk_div = v; }
     if (const char* ev = std::getenv("CTRFK_HOST_STREAMS")) { const int v = std::atoi(ev); if (v >= 1 && v <= ctr_fk_engine::kStreams) h->host_streams = v; }
-    h->host_zero_copy = 1;
+    h->host_zero_copy = 0;
     if (const char* ev = std::getenv("CTRFK_HOST_ZEROCOPY")) h->host_zero_copy = std::atoi(ev) != 0;
     if (const char* ev = std::getenv("CTRFK_HOST_CHUNK_WAVES")) { const int v = std::atoi(ev); if (v >= 1 && v <= 64) h->host_chunk_waves = v; }
     h->single_buf = nullptr;
@@ -358,19 +362,20 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     if (g.err != cudaSuccess) return cuda_fail("cudaSetDevice", g.err);
     std::lock_guard<std::mutex> lock(h->host_mu);
 
-    // ---- zero-copy form: page-locked host buffers are read and written by the solver kernel itself -------------
-    // One launch over the whole batch: every CTA fetches its joint vectors from host memory as whole lines, solves,
-    // stages its 128 poses in shared memory and writes them to host memory as whole lines (fk_tip_gather_kernel
-    // with the host buffer as its one destination).  No staging slabs, no chunk pipeline to fill and drain, reads
-    // and writes share the PCIe link in both directions for the whole run, and the transfers of one warp overlap
-    // the arithmetic of the other fifteen on its SM.  Taken when every buffer passed in is page-locked (pinned or
-    // registered) and 16-byte aligned, and the arithmetic is FAST; pageable memory, STRICT and
-    // CTR_FK_FLAG_HOST_STAGED take the chunked copy pipeline below.
+    // ---- zero-copy form (CTR_FK_FLAG_HOST_ZEROCOPY): page-locked host buffers are read and written by the solver
+    // kernel itself.  One launch over the whole batch: every CTA fetches its joint vectors from host memory as whole
+    // lines, solves, stages its 128 poses in shared memory and writes them to host memory as whole lines
+    // (fk_tip_gather_kernel with the host buffer as its one destination).  No staging slabs, no chunk pipeline to fill
+    // and drain.  Taken on request when every buffer passed in is page-locked (pinned or registered) and 16-byte
+    // aligned and the arithmetic is FAST.  It was the default while the tip kernel took 2.04 ms per 1M configurations
+    // (4.58e8 against 4.40e8 configurations/s for the copy pipeline); with the round-2 kernel (1.82 ms) the copy
+    // engines are ahead (4.76e8 against 4.60e8: SM stores cross PCIe in smaller packets than the DMA engines'), so
+    // the pipeline below is the default again and this form is for callers who want no device staging memory.
     // Step-mode batches that get binned stay on the staged form: binning permutes the rows of a CTA, and permuted
     // 96-byte rows would cross PCIe as scattered 16-byte writes (and the binning pass would read the joint vectors
     // over PCIe a second time).
     const bool binned = mode == CTR_FK_MODE_STEP && !(flags & CTR_FK_FLAG_NO_BINNING) && B >= kMinBinBatch && h->rb.maxs <= kMaxBinSamples;
-    if (h->host_zero_copy && !binned && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED | CTR_FK_FLAG_F32)) && tip && aligned16(jv) && aligned16(tip)) {
+    if ((h->host_zero_copy || (flags & CTR_FK_FLAG_HOST_ZEROCOPY)) && !binned && !(flags & (CTR_FK_FLAG_STRICT | CTR_FK_FLAG_HOST_STAGED | CTR_FK_FLAG_F32)) && tip && aligned16(jv) && aligned16(tip)) {
         const size_t nb = (size_t)B;
         double*  z_jv   = (double*)device_alias(jv, sizeof(double) * nb * h->njv);
         double*  z_tip  = (double*)device_alias(tip, sizeof(double) * nb * 12);
@@ -391,7 +396,8 @@ int ctr_fk_batch_host(ctr_fk_handle h, const double* jv, int64_t B, int mode, do
     const int NS = h->host_streams;
     // one chunk = one full wave of the tip kernel (3 or 4 CTAs of kBlock threads per SM): a chunk that
     // fills only part of the resident slots would pay a whole wave time for less work
-    const int64_t wave = (int64_t)h->sm_count * tip_blocks_per_sm(h->ntubes, h->desc.nsections) * kBlock * h->host_chunk_waves;
+    int64_t wave = (int64_t)h->sm_count * tip_blocks_per_sm(h->ntubes, h->desc.nsections) * kBlock * h->host_chunk_waves;
+    if (h->host_chunk_div > 1) wave = std::max<int64_t>(kBlock, wave / h->host_chunk_div / kBlock * kBlock);
     const int64_t chunk = std::min<int64_t>(wave > 0 ? wave : kHostChunk, B);
     const int njv = h->njv;
     // one slab per stream: jv | tip | n_out | step_out | status

@@ -20,6 +20,7 @@ FLAG_GATHER_ROWWISE = 0x400
 FLAG_HOST_STAGED = 0x800
 FLAG_RK4 = 0x1000
 FLAG_F32 = 0x2000
+FLAG_HOST_ZEROCOPY = 0x4000
 HOST_WRITE_COMBINED = 1
 FLAG_STRICT, FLAG_NO_BINNING, FLAG_SOA = 1, 2, 4
 E_NULL, E_DESC, E_ARG, E_XML, E_NOMEM, E_RANGE = -1, -2, -3, -4, -5, -6

@@ -301,7 +301,7 @@ def test_host_pointer_batch_and_single(ctrfk, oracle, robots, engines):
 
 @pytest.mark.parametrize("name", ["ctr_sec2_tub3.xml", "ctr_sec3_tub3.xml"])      # even and odd joint counts
 def test_host_pointer_zero_copy_form(ctrfk, oracle, robots, engines, name):
-    """ctr_fk_batch_host with page-locked buffers: ONE kernel reads the joint vectors from and writes every output to
+    """ctr_fk_batch_host with page-locked buffers and CTR_FK_FLAG_HOST_ZEROCOPY: ONE kernel reads the joint vectors from and writes every output to
     host memory directly.  Buffers from ctr_fk_host_alloc (NUMA-local, mapped; one write-combined) and from torch's
     pin_memory(); a batch whose last CTA is partial; an invalid configuration; all outputs.  Bit-equal to the staged
     form (CTR_FK_FLAG_HOST_STAGED) and to the device-pointer call, launches counted: 1 against one per chunk."""
@@ -320,9 +320,10 @@ def test_host_pointer_zero_copy_form(ctrfk, oracle, robots, engines, name):
     assert isinstance(eng.host_local_cpus(), str)
     for mode, kw in ((1, dict(nsamples=96)), (0, dict(step=d.max_length / 256.0, flags=ctrfk.FLAG_NO_BINNING))):
         l0 = ctrfk.launch_count()
-        eng.batch_host(jv, B, mode, tip=tip, n_out=n, step_out=st, status=status, **kw)
+        kwz = dict(kw); kwz["flags"] = kw.get("flags", 0) | ctrfk.FLAG_HOST_ZEROCOPY
+        eng.batch_host(jv, B, mode, tip=tip, n_out=n, step_out=st, status=status, **kwz)
         assert ctrfk.launch_count() - l0 == 1, "zero-copy form is one launch"
-        kw2 = dict(kw); kw2["flags"] = kw.get("flags", 0) | ctrfk.FLAG_HOST_STAGED
+        kw2 = dict(kw)                                              # the default: staged
         tip2 = np.zeros((B, 12)); n2 = np.zeros(B, np.int32); st2 = np.zeros(B); status2 = np.zeros(B, np.int32)
         l0 = ctrfk.launch_count()
         eng.batch_host(jv_np, B, mode, tip=tip2, n_out=n2, step_out=st2, status=status2, **kw2)

@@ -19,7 +19,7 @@ run() {   # N, extra args...
 }
 run 8 --steps 20 --warmup 5
 run 8 --steps 20 --warmup 5 --configs none --no-bind
-run 8 --steps 20 --warmup 5 --configs none --e2e-staged
+run 8 --steps 20 --warmup 5 --configs none --e2e-zerocopy
 for n in 4 2 1; do run $n --steps 20 --warmup 5 --configs none --no-cpu-baseline; done
 python - "$out" <<'PY'
 import json, sys
