@@ -222,18 +222,13 @@ void Robot::getRandomJointValues(CT_RNG& rng, CT_RND& rnd, VectorJ& jv, const Tr
 bool ProportionalScale::initialize(const Robot& robot)
 {
     if (!robot.init()) return false;
-    lengths_.clear();
-    total_ = 0.0;
+    std::vector<double> lengths;
     for (std::size_t s = 0; s < robot.getNSections(); ++s) {
         ctr_section_desc sd;
         if (!robot.getSection((unsigned)s, &sd)) return false;
-        lengths_.push_back(sd.length);
-        total_ += sd.length;
+        lengths.push_back(sd.length);
     }
-    section_ = 0;
-    room_ = total_;
-    redraw((double)std::rand() / (double)RAND_MAX);
-    return true;
+    return initialize(lengths);
 }
 
 bool Robot::setMaxSample(std::size_t maxSample)

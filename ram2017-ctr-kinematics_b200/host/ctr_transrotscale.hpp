@@ -85,6 +85,17 @@ class ProportionalScale : public TransRotScale {
 public:
     ProportionalScale() : lo_(1.0), hi_(1.0), inst_(1.0), total_(0.0), goal_(0.0), room_(0.0), section_(0), pos_(0) {}
     bool initialize(const Robot& robot);                     // section lengths from the robot; false if it has none
+    bool initialize(const std::vector<double>& sectionLengths)      // ... or handed in, base to tip
+    {
+        if (sectionLengths.empty()) return false;
+        lengths_ = sectionLengths;
+        total_ = 0.0;
+        for (double L : lengths_) total_ += L;
+        section_ = 0;
+        room_ = total_;
+        redraw((double)std::rand() / (double)RAND_MAX);
+        return true;
+    }
     void set_scale(const double& share) override { lo_ = hi_ = share; goal_ = total_ * share; }
     void set_scale(const double& a, const double& b)
     {

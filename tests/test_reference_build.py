@@ -267,6 +267,52 @@ def test_scale_policies_against_the_reference_classes(ctrfk, robots, refs):
     assert np.array_equal(got[1:, phi], lens * want[1:])
 
 
+def _load_facade_scale():
+    import ctypes as C, subprocess
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+    so, src = os.path.join(d, "libfacade_scale.so"), os.path.join(d, "facade_scale.cpp")
+    hdr = os.path.join(os.path.dirname(d), "..", "ram2017-ctr-kinematics_b200", "host", "ctr_transrotscale.hpp")
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.facade_gamma_scale.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.facade_proportional_scale.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.facade_scale_queue.argtypes = [C.c_void_p]
+    return lib
+
+
+def test_facade_scale_classes_equal_the_reference_classes(ctrfk, robots, refs):
+    """host/ctr_transrotscale.hpp — the GammaCorrection<LookUpSize> / ProportionalScale a caller of
+    ctrb200::Robot::getRandomJointValues(.., const TransRotScale&) hands in — against the reference's own classes
+    (transrotscale.h, compiled in oracle/_ref), the same uniform variates into both: bit for bit (both call std::pow)."""
+    import ctypes as C
+    lib = _load_facade_scale()
+    name = "ctr_sec3_tub4.xml"
+    d, ref = robots[name], refs[name]
+    rng = np.random.default_rng(3)
+    u = np.ascontiguousarray(rng.random(5000))
+    u[:3] = (0.0, 1.0, 0.5)
+    for lut in (0, 16, 64, 256, 1024):
+        for gamma in (0.5, 2.5):
+            got = np.zeros_like(u)
+            assert lib.facade_gamma_scale(lut, gamma, u.ctypes.data, u.size, got.ctypes.data) == 0
+            want = ref_lib.gamma_scale(lut, gamma, u)
+            assert np.array_equal(got, want), (lut, gamma)
+    S = d.nsections
+    lens = np.array([d.sec[s].length for s in range(S)])
+    B = 2000
+    us = np.ascontiguousarray(rng.random((B, S)))
+    got = np.zeros((B, S)); first = C.c_double(0.0)
+    assert lib.facade_proportional_scale(lens.ctypes.data, S, 0.3, 0.6, us.ctypes.data, B, got.ctypes.data, C.addressof(first)) == 0
+    want, first_ref = ref_lib.proportional_scale(ref, 0.3, 0.6, us)
+    assert 0.3 <= first.value <= 0.6 and 0.3 <= first_ref <= 0.6
+    assert np.array_equal(got[1:], want[1:])            # configuration 0 takes its goal from std::rand() in both
+    assert ((got >= 0.0) & (got <= 1.0)).all()
+    q = np.zeros(6)
+    lib.facade_scale_queue(q.ctypes.data)
+    assert list(q) == [3.0, 0.0, 2.0, 2.0, 4.0, 0.25]
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_jacobian_other_forms_bit_equal(ctrfk, oracle, robots, refs, name):
     """The ArcLengthStep form (robot_i.h:901-907: base pose from step mode, perturbed solves in NSamples mode with
