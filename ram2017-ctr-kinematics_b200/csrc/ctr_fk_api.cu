@@ -31,6 +31,8 @@ struct ctr_fk_engine {
     int            sm_count;
     static constexpr int kStreams = 8;      // created; ctr_fk_batch_host uses host_streams of them
     int            host_streams; // pipeline depth of the host-pointer path (4; CTRFK_HOST_STREAMS overrides, for tuning)
+    int            force_fine;   // -1: fine_sampling() decides which form of the sweep the tip kernels run; 0 / 1 force one
+                                 // (CTRFK_FORCE_FINE, for tests and tuning)
     int            host_chunk_div;   // ... divided by this (1; CTRFK_HOST_CHUNK_DIV, for tuning)
     int            host_chunk_waves; // chunk size of the host-pointer path in waves of the tip kernel (1; CTRFK_HOST_CHUNK_WAVES)
     int            host_zero_copy;   // take the zero-copy form of ctr_fk_batch_host without being asked by CTR_FK_FLAG_HOST_ZEROCOPY
@@ -154,6 +156,7 @@ int run_batch(ctr_fk_handle h, const double* jv, int64_t B, int mode, double ste
         a.order = order;
     }
     const bool strict = (flags & CTR_FK_FLAG_STRICT) != 0;
+    a.fine = (h->force_fine >= 0) ? h->force_fine : (fine_sampling(h->rb, mode, step, nsamples) ? 1 : 0);
     cudaError_t e;
     if (backbone) e = strict ? launch_backbone_strict(h->key, h->rb, a, st) : launch_backbone_fast(h->key, h->rb, a, st);
     else          e = strict ? launch_tip_strict(h->key, h->rb, a, st) : launch_tip_fast(h->key, h->rb, a, st);
@@ -210,6 +213,8 @@ int ctr_fk_create(const ctr_robot_desc* desc, int device, ctr_fk_handle* out)
     h->host_streams = 4;
     h->host_chunk_waves = 1;
     h->host_chunk_div = 1;
+    h->force_fine = -1;
+    if (const char* ev = std::getenv("CTRFK_FORCE_FINE")) { const int v = std::atoi(ev); if (v == 0 || v == 1) h->force_fine = v; }
     if (const char* ev = std::getenv("CTRFK_HOST_CHUNK_DIV")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) h->host_chunk_div = v; }
     if (const char* ev = std::getenv("CTRFK_HOST_STREAMS")) { const int v = std::atoi(ev); if (v >= 1 && v <= ctr_fk_engine::kStreams) h->host_streams = v; }
     h->host_zero_copy = 0;
@@ -296,6 +301,7 @@ int ctr_fk_batch_gather(ctr_fk_handle h, const double* jv, int64_t B, int mode, 
         if (eo != cudaSuccess) return cuda_fail("step-mode binning", eo);
         a.order = order;
     }
+    a.fine = (h->force_fine >= 0) ? h->force_fine : (fine_sampling(h->rb, mode, step, nsamples) ? 1 : 0);
     cudaError_t e = launch_tip_gather(h->key, h->rb, a, st);
     if (order) cudaFreeAsync(order, st);
     if (e != cudaSuccess) return cuda_fail("solver kernel launch", e);

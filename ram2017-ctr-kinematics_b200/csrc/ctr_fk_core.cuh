@@ -948,13 +948,12 @@ struct FastSweep {
     // units: w_t = h z_t, curvature weights (h/2) kgr (so x_t, y come out as components of psi), translation P / h.
     // Then d_t = w_t - w_0, the series run in m = |psi|^2 with the tables of run(), the step's quaternion is
     // (qa, qb psi) and its translation needs no h: 8 FP64 instructions fewer per step (113 -> 105 on the 3-tube
-    // robot), and the tier test needs no |alpha| reduction (only the middle tier evaluates sin/cos of an angle).  An
-    // iteration that is not hot converts the state back, runs run()'s own iteration and converts again (rare: coarse
-    // sampling, zero curvature); everything only that path needs (1/h, the step constants, h (1+nu) kappa) is
-    // recomputed there, so it does not occupy registers in the hot loop.  The sweep itself needs only sin/cos of the
-    // tube angles: a generic iteration gets the angles modulo 2 pi from the carried pair, and the angles themselves
-    // are accumulated only with KEEP_AL (when they are an output).  Same arithmetic per step as run() up to the
-    // placement of the factor h (FAST: results agree to rounding).
+    // robot), and the tier test needs no |alpha| reduction.  An iteration that is not hot (rare: coarse sampling,
+    // zero curvature) stays in these units too (scaled_step<.., false>); everything only that path needs (1/h, the
+    // step constants) is recomputed there, so it does not occupy registers in the hot loop.  The sweep itself needs
+    // only sin/cos of the tube angles — they are always advanced by rotating the carried pair — so the angles
+    // themselves are accumulated only with KEEP_AL (when they are an output), and the pose does not depend on that.
+    // Same arithmetic per step as run() up to the placement of the factor h (FAST: results agree to rounding).
     static constexpr int NG = S * (S + 1) / 2;
 #ifndef CTRK_SCALED_UNROLL
 #define CTRK_SCALED_UNROLL 2
@@ -971,25 +970,39 @@ struct FastSweep {
     static constexpr int kEmitUnroll = (T >= 4 || S >= 3) ? 2 : 1;
 #endif
 
-    // one hot iteration; dl[t] = w_t - w_0, (sxy, m) = |psi_xy|^2, |psi|^2 of the pending sample (pux, puy, puz = psi)
-    template <bool KEEP_AL>
-    CTR_HD void hot_scaled_step(const double* hg, const double* hko2, double* w, const double* dl, double sxy, double m)
+    // one iteration; dl[t] = w_t - w_0, (sxy, m) = |psi_xy|^2, |psi|^2 of the pending sample (pux, puy, puz = psi).
+    // HOT: both series apply (compile time; the flags are ignored).  Otherwise (rare: coarse sampling, zero curvature)
+    // se3_ok / rot_ok say which of them still does: the step of a sample outside the series' range comes from the
+    // generic step routine (handed u = 2 psi / h, its translation taken in units of h), and an angle increment
+    // outside the rotation series' range is applied with sin/cos of the increment itself — so no iteration ever
+    // needs the tube angles, and the state never leaves the units of the step.
+    template <bool KEEP_AL, bool HOT>
+    CTR_HD void scaled_step(const double* hg, const double* hko2, double* w, const double* dl, double sxy, double m,
+                            bool se3_ok, bool rot_ok)
     {
         // ---- (A) accumulate the pending sample -------------------------------------------------------------------
         if (want_tip) {
-            double qa = x_fma(CTRK_FC.qa4[0], m, CTRK_FC.qa4[1]);
-            double qb = x_fma(CTRK_FC.qb4[0], m, CTRK_FC.qb4[1]);
-            double qc = x_fma(CTRK_FC.qcs4[0], m, CTRK_FC.qcs4[1]);
-            qa = x_fma(qa, m, CTRK_FC.qa4[2]);
-            qb = x_fma(qb, m, CTRK_FC.qb4[2]);
-            qc = x_fma(qc, m, 2.0 / 3.0);                 // 4 (|phi| - sin|phi|) / |phi|^3
-            qa = x_fma(qa, m, CTRK_FC.qa4[3]);
-            qb = x_fma(qb, m, CTRK_FC.qb4[3]);
-            qa = x_fma(qa, m, 1.0);                       // cos(|phi|/2)
-            qb = x_fma(qb, m, 1.0);                       // sin(|phi|/2) / (|phi|/2)
-            const double ex = qb * pux, ey = qb * puy, ez = qb * puz;
-            const double cz = qc * puz;
-            apply(qa, ex, ey, ez, x_fma(cz, pux, qb * ey), x_fma(cz, puy, -(qb * ex)), x_fma(-qc, sxy, 1.0));
+            if (HOT || se3_ok) {
+                double qa = x_fma(CTRK_FC.qa4[0], m, CTRK_FC.qa4[1]);
+                double qb = x_fma(CTRK_FC.qb4[0], m, CTRK_FC.qb4[1]);
+                double qc = x_fma(CTRK_FC.qcs4[0], m, CTRK_FC.qcs4[1]);
+                qa = x_fma(qa, m, CTRK_FC.qa4[2]);
+                qb = x_fma(qb, m, CTRK_FC.qb4[2]);
+                qc = x_fma(qc, m, 2.0 / 3.0);                 // 4 (|phi| - sin|phi|) / |phi|^3
+                qa = x_fma(qa, m, CTRK_FC.qa4[3]);
+                qb = x_fma(qb, m, CTRK_FC.qb4[3]);
+                qa = x_fma(qa, m, 1.0);                       // cos(|phi|/2)
+                qb = x_fma(qb, m, 1.0);                       // sin(|phi|/2) / (|phi|/2)
+                const double ex = qb * pux, ey = qb * puy, ez = qb * puz;
+                const double cz = qc * puz;
+                apply(qa, ex, ey, ez, x_fma(cz, pux, qb * ey), x_fma(cz, puy, -(qb * ex)), x_fma(-qc, sxy, 1.0));
+            } else {
+                const double inv_h = 1.0 / c.h, inv_hh = 2.0 * inv_h;
+                const StepConsts kg = make_step_consts(c.h, rb.ztol);
+                double ew, ex, ey, ez, px_, py_, pz_;
+                se3_step_fast_k(pux * inv_hh, puy * inv_hh, puz * inv_hh, kg, ew, ex, ey, ez, px_, py_, pz_);
+                apply(ew, ex, ey, ez, px_ * inv_h, py_ * inv_h, pz_ * inv_h);
+            }
         }
         // ---- (B) this sample ------------------------------------------------------------------------------------
         bool in_k[S], in_c[S];
@@ -1037,16 +1050,23 @@ struct FastSweep {
         }
 #pragma unroll
         for (int t = 1; t < T; ++t) {
-            const double d  = dl[t];
-            const double d2 = d * d;
-            double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
-            double ps = x_fma(CTRK_FC.qb4[0], d2, CTRK_FC.qb4[1]);
-            pc = x_fma(pc, d2, CTRK_FC.qa4[2]);
-            ps = x_fma(ps, d2, CTRK_FC.qb4[2]);
-            pc = x_fma(pc, d2, CTRK_FC.qa4[3]);
-            ps = x_fma(ps, d2, CTRK_FC.qb4[3]);
-            const double cd = x_fma(pc, d2, 1.0);
-            const double sd = x_fma(d * d2, ps, d);
+            const double d = dl[t];
+            double cd, sd;
+            if (HOT || rot_ok) {
+                const double d2 = d * d;
+                double pc = x_fma(CTRK_FC.qa4[0], d2, CTRK_FC.qa4[1]);
+                double ps = x_fma(CTRK_FC.qb4[0], d2, CTRK_FC.qb4[1]);
+                pc = x_fma(pc, d2, CTRK_FC.qa4[2]);
+                ps = x_fma(ps, d2, CTRK_FC.qb4[2]);
+                pc = x_fma(pc, d2, CTRK_FC.qa4[3]);
+                ps = x_fma(ps, d2, CTRK_FC.qb4[3]);
+                cd = x_fma(pc, d2, 1.0);
+                sd = x_fma(d * d2, ps, d);
+            } else if ((hi_word(d) & 0x7fffffff) < 0x408f0000) {
+                sincos_bounded(d, sd, cd);                    // |d| < 992
+            } else {
+                fast_sincos(d, sd, cd);
+            }
             const double s1 = x_fma(cs[t], sd, sn[t] * cd);
             const double c1 = x_fma(-sn[t], sd, cs[t] * cd);
             sn[t] = s1; cs[t] = c1;
@@ -1055,7 +1075,14 @@ struct FastSweep {
         pos = x_sub(pos, c.h);
     }
 
-    template <bool KEEP_AL>
+    // FINE: the form for finely sampled sweeps (what the tip and gather kernels run when the launch's step is small,
+    // fine_sampling() below).  Its iterations outside the hot tier convert the state back, run run()'s own iteration
+    // and convert again — costly, but such iterations do not occur there, and the hot loop comes out 1-4 % faster than
+    // with the cold step in units of the step next to it (3 tubes 1.843 against 1.858 ms per 1M configurations, 3
+    // tubes in 3 sections 1.940 against 2.017, 5 tubes 2.729 against 2.750: equal instruction counts, fewer
+    // register-bank stalls — ncu dispatch stalls 0.15 against 0.23 per issue).  Coarse sampling is the other way round
+    // (N = 64: 1.21 against 0.82 ms), hence two forms.  Hot iterations are the same arithmetic in both.
+    template <bool KEEP_AL, bool FINE = false>
     CTR_HD void run_scaled()
     {
         const int n = c.n;
@@ -1095,7 +1122,7 @@ struct FastSweep {
             Px *= inv_h; Py *= inv_h; Pz *= inv_h;
         }
         // |psi|^2 = m is hot when zt2s < m < 2^-8; on the high words: hi(zt2s) < hi(m) < hi(2^-8), one unsigned range
-        // compare (a tie of the high words goes to the generic iteration, which compares exactly)
+        // compare (a tie of the high words goes to the generic step, which compares exactly)
         const unsigned m_lo = (unsigned)hi_word(zt2s) + 1u, m_span = 0x3f700000u - m_lo;
 #pragma unroll kScaledUnroll
         for (int k = n - 3; k >= 1; --k) {
@@ -1109,12 +1136,15 @@ struct FastSweep {
             const double sxy = x_fma(puy, puy, pux * pux);
             const double m   = x_fma(puz, puz, sxy);
             // hot: every |d_t| < 0.09375, zero tolerance <= |u|, (h|u|/2)^2 < 2^-8
-            const bool hot = dmax < kRotMaxHi && (!want_tip || ((unsigned)hi_word(m) - m_lo) < m_span);
+            const bool rot_ok = dmax < kRotMaxHi;
+            const bool se3_ok = !want_tip || ((unsigned)hi_word(m) - m_lo) < m_span;
 #ifdef CTRK_COUNT_COLD   /* host-side analysis builds only (tests/hostsim) */
-            ++g_iter_block; if (hot) ++g_iter_blockhot;
+            ++g_iter_block; if (rot_ok && se3_ok) ++g_iter_blockhot;
 #endif
-            if (hot) {
-                hot_scaled_step<KEEP_AL>(hg, hko2, w, dl, sxy, m);
+            if (rot_ok && se3_ok) {
+                scaled_step<KEEP_AL, true>(hg, hko2, w, dl, sxy, m, true, true);
+            } else if (!FINE) {
+                scaled_step<KEEP_AL, false>(hg, hko2, w, dl, sxy, m, se3_ok, rot_ok);
             } else {
                 // back to (u, z, P), one iteration of run(), and into units of the step again.  The generic
                 // iteration evaluates sin/cos of the tube angles; it gets them modulo 2 pi from the carried pair in
@@ -1143,7 +1173,7 @@ struct FastSweep {
                 Px *= inv_h; Py *= inv_h; Pz *= inv_h;
             }
         }
-        {
+        {   // back to (u, z, P) for the tail
             const double inv_h = 1.0 / h, inv_hh = 2.0 * inv_h;
             kc = make_step_consts(h, rb.ztol);
 #pragma unroll
@@ -1275,7 +1305,7 @@ CTR_HD void finish_tip(const KRobot& rb, const Ctl<L>& c, const Sweep& sw, doubl
 }
 
 // WANT_TIP = false skips the frame product (sample-only sweeps: STRICT backbone kernel, stability).
-template <class L, bool WANT_TIP, class OnSample>
+template <class L, bool WANT_TIP, class OnSample, bool FINE = false>
 CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* albase,
                        OnSample on_sample)
 {
@@ -1283,8 +1313,8 @@ CTR_HD void solve_fast(const KRobot& rb, const Ctl<L>& c, double* tip, double* a
     FastSweep<L, WANT_TIP, OnSample> sw(rb, c, on_sample);
     if (std::is_same<OnSample, NoSample>::value) {
         // nobody looks at the samples: the loop in units of the step; the tube angles themselves only if they are an output
-        if (albase) sw.template run_scaled<true>();
-        else        sw.template run_scaled<false>();
+        if (albase) sw.template run_scaled<true, FINE>();
+        else        sw.template run_scaled<false, FINE>();
     } else {
         sw.run();
     }

@@ -98,7 +98,8 @@ __device__ __forceinline__ void write_invalid(const FkArgs& a, int64_t cfg, int 
 // tubes get 3 CTAs and 168 registers (tip_blocks_per_sm, ctr_fk_launch.h).  Measured on B200 (tools/tune_tip.cu):
 // capping registers for 20 or 24 warps/SM is 3-5 % slower — the sweep is bound by FP64 issue, not by latency that
 // more warps could hide.
-template <class L, bool FAST>
+// FINE (FAST only): the form of the sweep for finely sampled launches (FastSweep::run_scaled, FkArgs::fine).
+template <class L, bool FAST, bool FINE = false>
 __global__ void __launch_bounds__(kBlock, FAST ? tip_blocks_per_sm(L::T, L::S) : 1)
 fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
@@ -123,7 +124,7 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
 
     double tip[12];
     double alb[L::T];
-    if (FAST) solve_fast<L, true>(rb, c, tip, a.alpha_base ? alb : nullptr, NoSample{});
+    if (FAST) solve_fast<L, true, NoSample, FINE>(rb, c, tip, a.alpha_base ? alb : nullptr, NoSample{});
     else      solve_strict<L, true>(rb, c, a.tip ? tip : nullptr, a.alpha_base ? alb : nullptr, NoSample{});
 
     if (a.tip) store_tf(a.tip + cfg * 12, tip);
@@ -149,7 +150,7 @@ fk_tip_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs 
 // consecutive in memory.  One thread storing its own 96-byte row makes 16-byte NVLink writes: fine with one
 // peer, 2.3x slower than no collective at all with seven (8 GPUs: 4.80 ms against 2.04 ms); kept for permuted
 // rows and as CTR_FK_FLAG_GATHER_ROWWISE for comparison.
-template <class L>
+template <class L, bool FINE = false>
 __global__ void __launch_bounds__(kBlock, tip_blocks_per_sm(L::T, L::S))
 fk_tip_gather_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ FkArgs a)
 {
@@ -196,7 +197,7 @@ fk_tip_gather_kernel(const __grid_constant__ KRobot rb, const __grid_constant__ 
         if (c.status) {
             write_invalid<L>(a, cfg, rb.maxs);                  // a.tip is null here: sample count, step, status only
         } else {
-            solve_fast<L, true>(rb, c, tip, nullptr, NoSample{});
+            solve_fast<L, true, NoSample, FINE>(rb, c, tip, nullptr, NoSample{});
             if (a.n_out) a.n_out[cfg] = c.nframes;
             if (a.step_out) a.step_out[cfg] = c.h;
             if (a.status) a.status[cfg] = 0;
@@ -376,7 +377,11 @@ fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_cons
     QT T;
     {
         FastSweep<L, true, NoSample> s1(rb, c, NoSample{});
-        s1.template run_scaled<true>();      // the tube angles are an output (alpha_base)
+        // the tube angles are an output (alpha_base).  Finely sampled launches run the loop in units of the step; coarse
+        // ones the generic loop that form falls back to anyway (no third copy of the sweep in this kernel: with one it
+        // ran 3 % slower at N = 256, 6.61 against 6.41 ms per 1M x 256 frames)
+        if (a.fine) s1.template run_scaled<true, true>();
+        else        s1.run();
         T.w = s1.Qw; T.x = s1.Qx; T.y = s1.Qy; T.z = s1.Qz; T.px = s1.Px; T.py = s1.Py; T.pz = s1.Pz;
         if (a.alpha_base) {
 #pragma unroll

@@ -18,7 +18,11 @@ cudaError_t launch_tip_fast(int key, const KRobot& rb, const FkArgs& args, cudaS
         grid = (unsigned)a.windows * (kBinWindow / kBlock);
     }
     switch (key) {
-#define X(S, A, Bq, C) CTRK_LAUNCH_CASE(fk_tip_kernel, true, S, A, Bq, C)
+#define X(S, A, Bq, C) \
+    case S * 1000 + A * 100 + Bq * 10 + C: \
+        if (a.fine) fk_tip_kernel<Lay<S, A, Bq, C>, true, true><<<grid, kBlock, 0, st>>>(rb, a); \
+        else        fk_tip_kernel<Lay<S, A, Bq, C>, true, false><<<grid, kBlock, 0, st>>>(rb, a); \
+        break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X
         default: return cudaErrorInvalidValue;

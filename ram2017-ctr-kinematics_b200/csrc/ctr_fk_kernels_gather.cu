@@ -19,7 +19,8 @@ cudaError_t launch_tip_gather(int key, const KRobot& rb, const FkArgs& args, cud
     switch (key) {
 #define X(S, A, Bq, C) \
     case S * 1000 + A * 100 + Bq * 10 + C: \
-        fk_tip_gather_kernel<Lay<S, A, Bq, C>><<<grid, kBlock, 0, st>>>(rb, a); \
+        if (a.fine) fk_tip_gather_kernel<Lay<S, A, Bq, C>, true><<<grid, kBlock, 0, st>>>(rb, a); \
+        else        fk_tip_gather_kernel<Lay<S, A, Bq, C>, false><<<grid, kBlock, 0, st>>>(rb, a); \
         break;
         CTRK_FOR_EACH_LAYOUT_K(X)
 #undef X

@@ -25,6 +25,7 @@ struct FkArgs {
     double*        backbone;    // [B][maxs][12] or [maxs][12][B]   nullable
     double*        radius;      // [B][maxs]     or [maxs][B]       nullable
     int            soa;         // backbone/radius layout
+    int            fine;        // tip / gather kernels: finely sampled launch (fine_sampling): the FINE form of the sweep
     int            windows;     // tip kernels, with `order`: number of binning windows; CTAs then walk the
                                 // windows rank-major (every window's longest sweeps first), 0 = linear
     // solve + all-gather in one kernel (ctr_fk_batch_gather): every pose goes to row gather_row + cfg of each
@@ -98,6 +99,20 @@ constexpr int backbone_blocks_per_sm(int, int) { return CTRK_BB_MINB; }
 // the sweep state want ~220 registers; with them the constant loads and register copies of the 168-register build go
 constexpr int backbone_blocks_per_sm(int ntubes, int nsections) { return (ntubes >= 4 || nsections >= 3) ? 2 : 3; }
 #endif
+// A launch is finely sampled when no iteration of its sweeps is expected outside the hot tier: the largest step of
+// the launch (the arc-length step itself, or MaxLength / N) times a bound on the torsion a tube can build up,
+// (1+nu) kappa^2 L, stays below 0.4 rad — N >= 160 on the shipped robots.  Only speed depends on it (which of two
+// forms of the same loop runs, FastSweep::run_scaled); it is a property of the call's arguments and the robot, never
+// of the batch, so every chunk and every rank of one logical call takes the same form.
+inline bool fine_sampling(const KRobot& rb, int mode, double step, int nsamples)
+{
+    double len = 0.0, kmax = 0.0, onu = 1.0;
+    for (int s = 0; s < rb.nsec; ++s) { len += rb.len[s]; kmax = kmax > (rb.kappa[s] < 0 ? -rb.kappa[s] : rb.kappa[s]) ? kmax : (rb.kappa[s] < 0 ? -rb.kappa[s] : rb.kappa[s]); }
+    for (int t = 0; t < kMaxTube; ++t) onu = onu > rb.onu[t] ? onu : rb.onu[t];
+    const int n = nsamples < rb.maxs ? nsamples : rb.maxs;
+    const double h = (mode == 0) ? step : (n > 0 ? len / (double)n : len);
+    return h * onu * kmax * kmax * len <= 0.4;
+}
 constexpr int kBinWindow = 4096;        // step-mode binning sorts windows of this many consecutive configurations
 
 // tip-only solvers (ctr_fk_kernels_fast.cu / ctr_fk_kernels_strict.cu)
@@ -108,6 +123,7 @@ cudaError_t launch_tip_f32(int key, const KRobot& rb, const FkArgs& a, cudaStrea
 // backbone solvers (two passes inside one kernel; the output buffer doubles as scratch)
 cudaError_t launch_backbone_fast(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 cudaError_t launch_backbone_fast_soa(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
+cudaError_t launch_backbone_fast_aos16(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 cudaError_t launch_backbone_strict(int key, const KRobot& rb, const FkArgs& a, cudaStream_t st);
 // finite-difference Jacobian (fast arithmetic)
 cudaError_t launch_jacobian(int key, const KRobot& rb, const JacArgs& a, cudaStream_t st);

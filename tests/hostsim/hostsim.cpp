@@ -61,6 +61,11 @@ void run(const KRobot& rb, const double* jv, int64_t B, int mode, double step, i
         } else if (fast == 5) {   // ... without the tube angles as an output (run_scaled<false>)
             solve_fast<L, true>(rb, c, t, nullptr, NoSample{});
             for (int q = 0; q < L::T; ++q) ab[q] = 0.0;
+        } else if (fast == 6) {   // the FINE form of that loop (what finely sampled launches of the tip kernel run)
+            solve_fast<L, true, NoSample, true>(rb, c, t, ab, NoSample{});
+        } else if (fast == 7) {
+            solve_fast<L, true, NoSample, true>(rb, c, t, nullptr, NoSample{});
+            for (int q = 0; q < L::T; ++q) ab[q] = 0.0;
         } else if (fast) solve_fast<L, true>(rb, c, t, ab, park);
         else             solve_strict<L, true>(rb, c, t, ab, park);
         if (tip) std::memcpy(tip + 12 * i, t, sizeof t);

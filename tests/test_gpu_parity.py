@@ -340,12 +340,12 @@ def test_host_pointer_zero_copy_form(ctrfk, oracle, robots, engines, name):
     # torch-pinned buffers take the same path; a binned step-mode batch and STRICT fall back to the staged form
     jvp = torch.from_numpy(jv_np).pin_memory(); tipp = torch.zeros(B, 12, dtype=torch.float64).pin_memory()
     l0 = ctrfk.launch_count()
-    eng.batch_host(jvp, B, 1, nsamples=96, tip=tipp)
+    eng.batch_host(jvp, B, 1, nsamples=96, tip=tipp, flags=ctrfk.FLAG_HOST_ZEROCOPY)
     assert ctrfk.launch_count() - l0 == 1
-    eng.batch_host(jv, B, 1, nsamples=96, tip=tip)
+    eng.batch_host(jv, B, 1, nsamples=96, tip=tip, flags=ctrfk.FLAG_HOST_ZEROCOPY)
     assert np.array_equal(tipp.numpy(), tip, equal_nan=True)
     l0 = ctrfk.launch_count()
-    eng.batch_host(jvp, B, 0, step=d.max_length / 256.0, tip=tipp)
+    eng.batch_host(jvp, B, 0, step=d.max_length / 256.0, tip=tipp, flags=ctrfk.FLAG_HOST_ZEROCOPY)
     assert ctrfk.launch_count() - l0 > 1
     for p in (p_jv, p_tip, p_n, p_st, p_status):
         eng.host_free(p)

@@ -30,7 +30,7 @@ def test_solvers_match_oracle(ctrfk, oracle, hostsim, robots, name, fast):
 
 
 @pytest.mark.parametrize("name", util.ROBOT_FILES)
-@pytest.mark.parametrize("fast", [4, 5], ids=["with_base_angles", "tip_only"])
+@pytest.mark.parametrize("fast", [4, 5, 6, 7], ids=["with_base_angles", "tip_only", "fine_with_base_angles", "fine_tip_only"])
 def test_scaled_loop_matches_oracle(ctrfk, oracle, hostsim, robots, name, fast):
     """FastSweep::run_scaled — the loop the tip, gather, Jacobian (tip forms) and stability kernels run when nobody
     looks at the samples: state in units of the step, tube angles not accumulated in the tip-only form.  Same gate as
@@ -47,7 +47,7 @@ def test_scaled_loop_matches_oracle(ctrfk, oracle, hostsim, robots, name, fast):
         assert np.array_equal(o["n"], s["n"]) and np.array_equal(o["step"], s["step"])
         dp, ang = util.pose_errors(o["tip"], s["tip"])
         assert dp.max() < 2e-10 and ang.max() < 1e-11, (mode, kw, dp.max(), ang.max())
-        if fast == 4:
+        if fast in (4, 6):
             assert np.abs(o["alpha_base"] - s["alpha_base"]).max() < 1e-10
         # ... and against the loop it replaces: the same arithmetic up to the placement of the factor h
         r = util.hostsim_fk(hostsim, d, jv, mode, fast=1, **kw)
@@ -62,9 +62,14 @@ def test_scaled_loop_pose_does_not_depend_on_the_base_angle_output(ctrfk, hostsi
     d = robots["ctr_sec3_tub5.xml"]
     jv = ctrfk.sample_joints_host(d, 5, 0, 4000)
     for n in (24, 48, 128, 256):
-        a = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=n, fast=4)
-        b = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=n, fast=5)
-        assert np.array_equal(a["tip"], b["tip"])
+        for with_al, without in ((4, 5), (6, 7)):              # both forms of the loop (coarse / FINE)
+            a = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=n, fast=with_al)
+            b = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=n, fast=without)
+            assert np.array_equal(a["tip"], b["tip"])
+    # where every iteration is hot (fine sampling) the two forms are the same arithmetic
+    a = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=256, fast=5)
+    b = util.hostsim_fk(hostsim, d, jv, ctrfk.MODE_NSAMPLE, nsamples=256, fast=7)
+    assert np.array_equal(a["tip"], b["tip"])
 
 
 def test_coarse_steps_take_the_closed_form_branch(ctrfk, oracle, hostsim, robots):
