@@ -1079,8 +1079,8 @@ struct FastSweep {
     // fine_sampling() below).  Its iterations outside the hot tier convert the state back, run run()'s own iteration
     // and convert again — costly, but such iterations do not occur there, and the hot loop comes out 1-4 % faster than
     // with the cold step in units of the step next to it (3 tubes 1.843 against 1.858 ms per 1M configurations, 3
-    // tubes in 3 sections 1.940 against 2.017, 5 tubes 2.729 against 2.750: equal instruction counts, fewer
-    // register-bank stalls — ncu dispatch stalls 0.15 against 0.23 per issue).  Coarse sampling is the other way round
+    // tubes in 3 sections 1.940 against 2.017, 5 tubes 2.729 against 2.750: equal instruction counts, a matter of
+    // how ptxas allocates and schedules the loop next to a large or a small cold block).  Coarse sampling is the other way round
     // (N = 64: 1.21 against 0.82 ms), hence two forms.  Hot iterations are the same arithmetic in both.
     template <bool KEEP_AL, bool FINE = false>
     CTR_HD void run_scaled()

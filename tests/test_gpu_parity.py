@@ -351,6 +351,44 @@ def test_host_pointer_zero_copy_form(ctrfk, oracle, robots, engines, name):
         eng.host_free(p)
 
 
+@pytest.mark.parametrize("name", util.ROBOT_FILES)
+def test_both_forms_of_the_sweep_loop(ctrfk, oracle, robots, name, monkeypatch):
+    """The tip and gather kernels run one of two forms of FastSweep::run_scaled, chosen per launch by fine_sampling()
+    (ctr_fk_launch.h).  Forced either way (CTRFK_FORCE_FINE, read at ctr_fk_create): with fine sampling every
+    iteration is hot and the two forms are the same arithmetic — bit-identical poses; with coarse sampling both stay
+    inside the gate against the oracle.  So the choice only ever changes speed."""
+    d = robots[name]
+    B = 50_000
+    jv = ctrfk.sample_joints_host(d, util.SEEDS[name] + 11, 0, B)
+    res = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("CTRFK_FORCE_FINE", force)
+        eng = ctrfk.Engine(d, 0)
+        res[force] = {n: run_gpu(ctrfk, eng, jv, 1, nsamples=n) for n in (256, 40)}
+        res[force]["step"] = run_gpu(ctrfk, eng, jv, 0, step=d.max_length / 256.0)
+        eng.close()
+    monkeypatch.delenv("CTRFK_FORCE_FINE")
+    for key in (256, "step"):
+        # bit-identical wherever every iteration was hot — all but a few configurations per 10 000 (ctr_sec3_tub5's
+        # soft inner tubes turn fastest) — and to rounding on the rest
+        same = (res["0"][key]["tip"] == res["1"][key]["tip"]).all(axis=1)
+        dp, ang = util.pose_errors(res["0"][key]["tip"], res["1"][key]["tip"])
+        util.record("sweep_loop_forms", dict(robot=name, case=str(key), identical=float(same.mean()), max_dp=float(dp.max()), max_ang=float(ang.max())))
+        assert same.mean() >= 0.999 and dp.max() < 1e-12 and ang.max() < 1e-12, (key, same.mean(), dp.max(), ang.max())
+        assert np.array_equal(res["0"][key]["n"], res["1"][key]["n"])
+    o = oracle.fk_batch(d, jv, 1, nsamples=40)
+    for force in ("0", "1"):
+        assert np.array_equal(o["n"], res[force][40]["n"])
+        dp, ang = util.pose_errors(o["tip"], res[force][40]["tip"])
+        assert dp.max() <= util.TOL_POS and ang.max() <= util.TOL_ROT, (force, dp.max(), ang.max())
+        assert np.abs(o["alpha_base"] - res[force][40]["alpha_base"]).max() < 1e-9
+    # the automatic choice: N = 256 is a fine launch, N = 40 a coarse one, on every shipped robot
+    eng = ctrfk.Engine(d, 0)
+    assert np.array_equal(run_gpu(ctrfk, eng, jv, 1, nsamples=256)["tip"], res["1"][256]["tip"])
+    assert np.array_equal(run_gpu(ctrfk, eng, jv, 1, nsamples=40)["tip"], res["0"][40]["tip"])
+    eng.close()
+
+
 def test_device_sampler_equals_host_sampler(ctrfk, robots, engines):
     st = torch.cuda.current_stream().cuda_stream
     for name in util.ROBOT_FILES:
