@@ -22,7 +22,7 @@ def load_hostsim():
     so = os.path.join(d, "libhostsim.so")
     src = os.path.join(d, "hostsim.cpp")
     csrc = os.path.join(REPO, "ram2017-ctr-kinematics_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("ctr_fk_core.cuh", "ctr_fk_core_f32.cuh", "ctr_fk_krobot.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("ctr_fk_core.cuh", "ctr_fk_core_f32.cuh", "ctr_fk_core_f32x2.cuh", "ctr_fk_krobot.h")]
     if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-march=x86-64-v3", "-ffp-contract=off",
                                "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
