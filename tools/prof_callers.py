@@ -49,7 +49,7 @@ runs = [
     ("jacobian iSample form N=256, iSample=128", B, lambda: eng.jacobian_ex(jv, B, 1, 1e-5, 1e-4, jac, nsamples=256, i_sample=128,
                                                                             jac_sample=jacs, tip=tip, sample=smp, stream=st)),
     ("stability dAlpha=0.1 step=L/256", 50_000, lambda: eng.stability(jv, 50_000, 0.1, d.max_length / 256.0, -1.0, stable, deg, st)),
-    ("base-angle shooting N=256", B, lambda: eng.batch_base(jv, B, 1, nsamples=256, jv_tip=jt, tip=tip, iters=it, status=stt, stream=st)),
+    ("base-angle shooting N=256", B, lambda: eng.batch_base(jv, B, 1, nsamples=256, max_iter=24, jv_tip=jt, tip=tip, iters=it, status=stt, stream=st)),
 ]
 for name, n, fn in runs:
     ms = timed(fn)
