@@ -1083,10 +1083,12 @@ struct FastSweep {
     // how ptxas allocates and schedules the loop next to a large or a small cold block).  Coarse sampling is the other way round
     // (N = 64: 1.21 against 0.82 ms), hence two forms.  Hot iterations are the same arithmetic in both.
     template <bool KEEP_AL, bool FINE = false>
-    CTR_HD void run_scaled()
+    CTR_HD void run_scaled(bool generic = false)
     {
         const int n = c.n;
-        if (n < 8 || !(c.h > 1e-150)) { run(); return; }      // short sweeps; a retracted robot (h = 0) has no 1 / h
+        // short sweeps; a retracted robot (h = 0) has no 1 / h; callers that want run() for coarse launches without a
+        // second inlined copy of it (the backbone kernel)
+        if (n < 8 || !(c.h > 1e-150) || generic) { run(); return; }
         double dl[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) dl[t] = 0.0;

@@ -379,9 +379,8 @@ fk_backbone_twosweep_kernel(const __grid_constant__ KRobot rb, const __grid_cons
         FastSweep<L, true, NoSample> s1(rb, c, NoSample{});
         // the tube angles are an output (alpha_base).  Finely sampled launches run the loop in units of the step; coarse
         // ones the generic loop that form falls back to anyway (no third copy of the sweep in this kernel: with one it
-        // ran 3 % slower at N = 256, 6.61 against 6.41 ms per 1M x 256 frames)
-        if (a.fine) s1.template run_scaled<true, true>();
-        else        s1.run();
+        // ran 3 % slower at N = 256, 6.61 against 6.41 ms per 1M x 256 frames), through its one inlined call site
+        s1.template run_scaled<true, true>(/*generic=*/!a.fine);
         T.w = s1.Qw; T.x = s1.Qx; T.y = s1.Qy; T.z = s1.Qz; T.px = s1.Px; T.py = s1.Py; T.pz = s1.Pz;
         if (a.alpha_base) {
 #pragma unroll
